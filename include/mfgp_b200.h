@@ -1,0 +1,149 @@
+/* mfgp_b200 -- C ABI of the B200-native multi-fidelity GP hot path.
+ *
+ * The reference (MartinKlapacz/multifidelity-datafusion-GPs) has no FFI: its hot path is the
+ * Python object protocol of GPy.models.GPRegression, reached from
+ *   src/MFDataFusion.py:93-100   (construction = inference, then AbstractMFGP.ARD)
+ *   src/abstractMFGP.py:131-137  (optimize / optimize_restarts -> one LML+gradient per step)
+ *   src/MFDataFusion.py:153-156  (augment, then hf_model.predict)
+ *   src/abstractMFGP.py:100-104  (low-fidelity GP and its mean predictor f_low)
+ *   src/abstractMFGP.py:124-129  (acquisition: argmax of the predictive variance)
+ * Each entry point below names the reference call it replaces.  The host side that binds them
+ * (ctypes) is multifidelity_datafusion_gps_b200/_ffi.py; INTEGRATION.md shows the binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *  - All arithmetic is FP64, indices are int64.  Matrices are row-major.
+ *  - Pointers named d_* are DEVICE pointers owned by the caller (torch tensors' data_ptr());
+ *    pointers named h_* are HOST pointers.  The library owns only the opaque handle, which holds
+ *    a fixed-size scratch allocated in mfgp_create -- no allocation happens in any other call.
+ *  - Every call enqueues on the handle's stream (mfgp_set_stream).  Calls with h_* outputs
+ *    synchronise that stream before returning; all other calls are asynchronous.
+ *  - Return value: 0 ok; >0 LAPACK-style info (1-based index of the first non-positive pivot of
+ *    the Cholesky factorisation) so the host can replay GPy's jitter schedule; <0 bad argument or
+ *    CUDA failure (message via mfgp_last_error).  There is no CPU fallback.
+ *  - "Npad" = mfgp_padded_n(N): N rounded up to a multiple of 128.  Factor buffers are
+ *    Npad x Npad with leading dimension Npad; the pad block is the identity.
+ *  - theta (HOST, P doubles):  kind=MFGP_KIND_COMPOSITE, P=7:
+ *        [var1, len1 | var2, len2 | var3, len3 | noise]   K = k1(z,z')k2(x,x') + k3(x,x')
+ *    kind=MFGP_KIND_RBF, P=3: [var, len | noise].   x = first d columns, z = columns d..D-1.
+ */
+#ifndef MFGP_B200_H
+#define MFGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFGP_KIND_RBF 0        /* GPy.kern.RBF(D)          src/abstractMFGP.py:59-60 */
+#define MFGP_KIND_COMPOSITE 1  /* RBF(z)*RBF(x) + RBF(x)   src/abstractMFGP.py:62-80 */
+
+#define MFGP_UPLO_LOWER 0
+#define MFGP_UPLO_FULL 1
+
+#define MFGP_MAX_D 32          /* augmented input width d + E */
+#define MFGP_MAX_E 16
+
+typedef struct mfgp_ctx* mfgp_handle_t;
+
+/* One fitted GP level: what GPy keeps in GPRegression after inference (X, kernel parameters,
+ * posterior woodbury_vector = alpha, woodbury_chol = L; we keep W = L^-1 instead of L). */
+typedef struct {
+  int32_t kind;          /* MFGP_KIND_* */
+  int32_t N;             /* training points */
+  int32_t D;             /* columns of X */
+  int32_t d;             /* leading columns that are the plain inputs x */
+  int32_t P;             /* len(theta) */
+  int32_t reserved;
+  const double* d_X;     /* (N, D) row-major */
+  const double* h_theta; /* HOST (P,) */
+  const double* d_W;     /* (Npad, Npad) lower-triangular L^-1, ld = Npad; may be NULL for mean-only use */
+  const double* d_alpha; /* (Npad,)  K_y^-1 y, zero padded */
+} mfgp_level_t;
+
+int mfgp_version(void);
+int mfgp_padded_n(int N);
+
+int mfgp_create(int device, mfgp_handle_t* out);
+int mfgp_destroy(mfgp_handle_t h);
+int mfgp_set_stream(mfgp_handle_t h, void* cuda_stream);
+const char* mfgp_last_error(mfgp_handle_t h);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+long long mfgp_launch_count(mfgp_handle_t h);
+
+/* K1 -- covariance assembly.  Replaces kern.K(X) + diag.add(Ky, noise + 1e-8)
+ * (GPy exact_gaussian_inference.py, reached from src/MFDataFusion.py:93-98).
+ * Writes K_y = K + (noise + 1e-8 + jitter) I into d_K (N x N, leading dimension ldk);
+ * uplo=LOWER writes the lower triangle including the diagonal only. */
+int mfgp_assemble(mfgp_handle_t h, int kind, const double* d_X, int N, int D, int d,
+                  const double* h_theta, int P, double jitter, double* d_K, long long ldk, int uplo);
+
+/* K2+K3 -- factorise and solve.  Replaces pdinv(Ky) / dpotrs (GPy exact_gaussian_inference.py)
+ * as run by GPRegression construction (src/MFDataFusion.py:93-98, src/abstractMFGP.py:100-102).
+ * d_A, d_W: (Npad, Npad) caller buffers; on return d_A holds L (lower; upper triangle undefined),
+ * d_W holds L^-1, d_alpha (Npad) holds K_y^-1 y.  h_out[0..2] = {LML, logdet, y^T alpha}. */
+int mfgp_factorize(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N, int D,
+                   int d, const double* h_theta, int P, double jitter, double* d_A, double* d_W,
+                   double* d_alpha, double* h_out);
+
+/* K1..K5 -- one log-marginal-likelihood + gradient evaluation at fixed theta: the objective
+ * paramz evaluates once per L-BFGS-B step (src/abstractMFGP.py:134,137).
+ * On return d_A holds K_y^-1 (lower triangle), d_W holds L^-1, d_alpha holds alpha.
+ * h_lml[0] = LML; h_grad[0..P-1] = dLML/dtheta (untransformed, ordered as theta). */
+int mfgp_lml_grad(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N, int D,
+                  int d, const double* h_theta, int P, double jitter, double* d_A, double* d_W,
+                  double* d_alpha, double* h_lml, double* h_grad);
+
+/* Same evaluation with per-stage CUDA-event timings (ms) for bench.py / the roofline report:
+ * h_ms[0..5] = {assemble, potrf, trtri, solve(alpha), K^-1 = W^T W, grad_reduce}. */
+int mfgp_lml_grad_timed(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N,
+                        int D, int d, const double* h_theta, int P, double jitter, double* d_A,
+                        double* d_W, double* d_alpha, double* h_lml, double* h_grad, double* h_ms);
+
+/* Building blocks exposed for the parity tests (LAPACK names, lower, row-major, n multiple of 128). */
+int mfgp_potrf(mfgp_handle_t h, double* d_A, double* d_W, int npad);   /* A -> L; W diag blocks -> leaf inverses */
+int mfgp_trtri(mfgp_handle_t h, const double* d_L, double* d_W, int npad); /* completes W = L^-1 (after mfgp_potrf) */
+int mfgp_lauum(mfgp_handle_t h, const double* d_W, double* d_Kinv, int npad); /* Kinv(lower) = W^T W */
+
+/* K6 -- prediction.  Replaces GP.predict -> Posterior._raw_predict (src/MFDataFusion.py:156,
+ * src/abstractMFGP.py:104): mean = Kx^T alpha; var = max(Kxx - |W Kx|^2, 1e-15) (+ noise).
+ * d_Xnew: (M, D).  d_var may be NULL (mean only, no W needed).  d_ws/ws_bytes: caller scratch for
+ * the cross-covariance chunk, at least mfgp_predict_ws_bytes(N, 128). */
+size_t mfgp_predict_ws_bytes(int N, long long cols);
+int mfgp_predict(mfgp_handle_t h, const mfgp_level_t* gp, const double* d_Xnew, long long M,
+                 double* d_mean, double* d_var, int include_noise, double* d_ws, size_t ws_bytes);
+
+/* A1 with a data-driven low-fidelity level.  Replaces __augment_Data (src/MFDataFusion.py:177-208)
+ * when f_low is lf_model.predict(.)[0] (src/abstractMFGP.py:104):
+ * Xaug[i] = [x_i, mu_l(x_i + o_0 tau), ..., mu_l(x_i + o_{E-1} tau)].  h_offsets: HOST (E, d). */
+int mfgp_augment(mfgp_handle_t h, const mfgp_level_t* lf, const double* d_X, long long M,
+                 const double* h_offsets, int E, double tau, double* d_Xaug, double* d_ws,
+                 size_t ws_bytes);
+
+/* K7 -- Monte-Carlo propagation of the low-fidelity posterior (extension; README.md:13).
+ * For every test point m (global index m0 + m) and sample s: z = mu_l + sd_l * eps,
+ * (mu_s, v_s) = HF predict at [x, z]; mean = mean_s mu_s; var = mean_s v_s + var_s(mu_s).
+ * d_eps: (M, S) standard normals, or NULL -> Philox4x32-10 keyed by seed, counter = (m0+m)*S+s.
+ * d_weights: optional (M,) quadrature weights; h_wsum[0] += sum_m w_m mean_m (PCE mean).
+ * Only E = 1 (NARGP: offsets = {0}) is supported by this entry point. */
+int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
+                    const double* d_Xtest, long long M, int S, const double* d_eps,
+                    unsigned long long seed, long long m0, int include_lf_noise,
+                    int include_hf_noise, const double* d_weights, double* d_mean, double* d_var,
+                    double* h_wsum, double* d_ws, size_t ws_bytes);
+
+/* the eps the in-kernel generator uses, for the parity tests: out[i] = N(0,1) of counter first+i */
+int mfgp_fill_normal(mfgp_handle_t h, unsigned long long seed, long long first, long long count,
+                     double* d_out);
+
+/* K8 -- acquisition.  Replaces AbstractMaximizer.maximize's objective scan
+ * (src/adaptation_maximizers/scipydirect_wrapper.py:22-26) by a candidate-set argmax:
+ * h_val[0] = max_i v[i], h_idx[0] = lowest i attaining it (np.argmax semantics). */
+int mfgp_argmax(mfgp_handle_t h, const double* d_v, long long C, double* h_val, long long* h_idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFGP_B200_H */

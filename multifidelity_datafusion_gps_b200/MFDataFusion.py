@@ -1,0 +1,252 @@
+"""MultifidelityDataFusion -- the reference's concrete model (src/MFDataFusion.py:13-208) on the
+B200 GP engine.  Same constructor, same ``fit / adapt / predict / get_mse`` contracts (NumPy in,
+NumPy out, ``assert``-based validation).  What changes underneath:
+
+* ``__augment_Data`` (:177-208): the reference maps a Python lambda over rows twice; here a callable
+  ``f_low`` is evaluated ONCE on all M*E augmented locations (host, vectorised), and a data-driven
+  low-fidelity GP is evaluated on the GPU for all locations in one batched kernel (mfgp_augment).
+* ``fit`` (:75-100): every LML+gradient of the ARD recipe is one GPU evaluation.
+* ``predict`` (:141-156): fused cross-covariance -> mean -> W Kx -> variance on the GPU.
+
+Extensions (keyword-only, defaults reproduce the reference):
+* ``predict_mc``  Monte-Carlo propagation of the low-fidelity posterior (README.md:13; absent in the
+  reference, which collapses the LF level to its mean, src/abstractMFGP.py:104).
+* ``acquisition_argmax``  candidate-set arg-max of the predictive variance (used by
+  ``CandidateSetMaximizer``), optionally sharded over ranks.
+* ``broadcast_state``  NCCL broadcast of the fitted state so that other ranks can predict.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _ffi, dist, gp
+from .abstractMFGP import AbstractMFGP
+from .adaptation_maximizers import AbstractMaximizer, ScipyDirectMaximizer
+from .augm_iterators import BackwardAugmentation
+
+
+class MultifidelityDataFusion(AbstractMFGP):
+    """Regression model for a scarce/precise (high-fidelity) and an abundant/imprecise (low-fidelity)
+    data source; see the reference docstring (src/MFDataFusion.py:14-54) for the parameters."""
+
+    def __init__(self, name: str, input_dim: int, num_derivatives: int, tau: float, f_exact: callable,
+                 lower_bound: np.ndarray = None, upper_bound: float = None, f_low: callable = None,
+                 lf_X: np.ndarray = None, lf_Y: np.ndarray = None, lf_hf_adapt_ratio: int = 1,
+                 use_composite_kernel: bool = True, adapt_maximizer: AbstractMaximizer = None,
+                 eps: float = 1e-8, add_noise: bool = False):
+        if adapt_maximizer is None:
+            adapt_maximizer = ScipyDirectMaximizer()      # the reference's default (:59)
+        super().__init__(name=name, input_dim=input_dim, num_derivatives=num_derivatives, tau=tau,
+                         f_exact=f_exact, lower_bound=lower_bound, upper_bound=upper_bound, f_low=f_low,
+                         lf_X=lf_X, lf_Y=lf_Y, lf_hf_adapt_ratio=lf_hf_adapt_ratio,
+                         use_composite_kernel=use_composite_kernel, adapt_maximizer=adapt_maximizer,
+                         eps=eps)
+        self.augm_iterator = BackwardAugmentation(self.num_derivatives, dim=input_dim)
+        self.initialize_kernel(use_composite_kernel)
+        self.initialize_lf_level(f_low, lf_X, lf_Y)
+        self.add_noise = add_noise
+        self.device = gp.current_device()
+
+    # -- A5 fit -----------------------------------------------------------------------------------
+    def fit(self, hf_X, theta=None):
+        """Fit the high-fidelity GP on the augmented inputs.  ``theta`` (extension): skip the
+        optimiser and install these hyper-parameters (parity tests at fixed theta)."""
+        assert hf_X.ndim == 2, "invalid input shape"
+        assert hf_X.shape[1] == self.input_dim, "invalid input dim"
+        self.hf_X = hf_X
+        self.hf_Y = self.f_exact(self.hf_X)
+        assert self.hf_Y.shape == (self.hf_X.shape[0], 1)
+        self.hf_model = gp.GPRegression(X=self.__augment_Data(self.hf_X), Y=self.hf_Y,
+                                        kernel=self.kernel, initialize=True)
+        if theta is None:
+            self.ARD(self.hf_model, 6)
+        else:
+            self.hf_model._set_params(np.asarray(theta, dtype=np.float64))
+
+    # -- A10 adapt --------------------------------------------------------------------------------
+    def adapt(self, adapt_steps: int, plot_mode: str = None, X_test: np.ndarray = None,
+              Y_test: np.ndarray = None, eps: float = 1e-8):
+        """Acquire `adapt_steps` new high-fidelity points where the predictive variance is largest.
+        plot_mode is accepted for compatibility ('u','m','e','um','mu',None); nothing is drawn."""
+        self.adapt_steps = adapt_steps
+        self.X_test = X_test
+        self.Y_test = Y_test
+        self.eps = eps
+        # The reference calls self.__adapt_lf() here for a data-driven LF level, a method that does
+        # not exist (AttributeError).  Low-fidelity adaptation is skipped.
+        modes = {'u': dict(plot_uncertainties=True), 'm': dict(plot_means=True), 'e': dict(plot_error=True),
+                 'um': dict(plot_means=True, plot_uncertainties=True),
+                 'mu': dict(plot_means=True, plot_uncertainties=True), None: dict()}
+        assert plot_mode in modes.keys(), "Invalid plot mode. Select one of these: {}".format(list(modes.keys()))
+        self.adapt_and_plot(**modes[plot_mode])
+
+    # -- A6 predict -------------------------------------------------------------------------------
+    def predict(self, X_test):
+        """(mean (M,1), variance (M,1)); the variance includes the noise variance (GPy semantics)."""
+        assert X_test.ndim == 2
+        assert X_test.shape[1] == self.input_dim
+        mean, var = self._predict_device(gp.to_device(X_test, self.device))
+        return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]
+
+    def _apply_add_noise(self):
+        if self.add_noise:                                  # :154-155: re-inference at noise 1e-6
+            if self.hf_model.likelihood.variance != 1e-6:
+                self.hf_model.likelihood.variance = 1e-6
+
+    def _predict_device(self, dX):
+        dXa = self._augment_device(dX)
+        self._apply_add_noise()
+        return self.hf_model.predict_device(dXa, True, True)
+
+    def get_mse(self, X_test, Y_test):
+        assert len(X_test) == len(Y_test), 'unequal number of X and y values'
+        assert X_test.shape[1] == self.input_dim, 'wrong input value dimension'
+        assert Y_test.shape[1] == 1, 'target values must be scalars'
+        preds, _ = self.predict(X_test)
+        return float(np.mean((np.asarray(Y_test) - preds) ** 2))
+
+    # -- A1 augmentation --------------------------------------------------------------------------
+    def _f_low_batched(self, locations):
+        """Host callable f_low on (rows, d) locations -> (rows,).  One vectorised call; if the
+        callable is not row-vectorised, fall back to the reference's per-group calls (:197)."""
+        M, E = locations.shape[0], locations.shape[1]
+        flat = locations.reshape(M * E, self.input_dim)
+        try:
+            vals = np.asarray(self.f_low(flat), dtype=np.float64)
+            if vals.size == M * E:
+                return vals.reshape(M, E)
+        except Exception:
+            pass
+        vals = np.array([np.asarray(self.f_low(loc), dtype=np.float64).reshape(E) for loc in locations])
+        return vals
+
+    def _augment_device(self, dX):
+        """(M, d) CUDA tensor -> (M, d+E) CUDA tensor."""
+        M = int(dX.shape[0])
+        offsets = self.augm_iterator.offset_table()
+        E = offsets.shape[0]
+        if self.data_driven_lf_approach:
+            h = _ffi.get_handle(self.device)
+            lvl = self.lf_model.level_struct()
+            out = torch.empty((M, self.input_dim + E), dtype=torch.float64, device=dX.device)
+            per_row = E * (self.input_dim + 1) * 8
+            ws = gp.workspace(self.device, max(min(M, 1 << 20) * per_row, 4096))
+            offs = np.ascontiguousarray(offsets, dtype=np.float64)
+            h.check(h.lib.mfgp_augment(h.h, ctypes.byref(lvl), dX.data_ptr(), M,
+                                       offs.ctypes.data_as(ctypes.c_void_p), E, float(self.tau),
+                                       out.data_ptr(), ws.data_ptr(), ws.numel() * 8))
+            return out
+        X = dX.cpu().numpy()
+        locations = X[:, None, :] + offsets[None, :, :] * self.tau
+        Xa = np.concatenate([X, self._f_low_batched(locations)], axis=1)
+        return gp.to_device(Xa, self.device)
+
+    def __augment_Data(self, X):
+        """X (M,d) -> [X, f_low(x + o_0 tau), ..., f_low(x + o_{E-1} tau)]  (M, d+E), NumPy."""
+        assert X.shape == (len(X), self.input_dim)
+        E = self.augm_iterator.new_entries_count()
+        if self.data_driven_lf_approach:
+            Xa = self._augment_device(gp.to_device(X, self.device)).cpu().numpy()
+        else:
+            offsets = self.augm_iterator.offset_table()
+            locations = X[:, None, :] + offsets[None, :, :] * self.tau
+            assert locations.shape == (len(X), E, self.input_dim)
+            Xa = np.concatenate([X, self._f_low_batched(locations)], axis=1)
+        assert Xa.shape == (len(X), E + self.input_dim)
+        return Xa
+
+    augment_data = __augment_Data
+
+    # -- A8 Monte-Carlo propagation (extension) ------------------------------------------------------
+    def predict_mc_device(self, dX, n_samples=100, d_eps=None, seed=0, m0=0, d_weights=None,
+                          include_lf_noise=True, ws_bytes=None):
+        """dX (M,d) CUDA -> (mean (M,), var (M,), weighted sum or None).  d_eps: optional (M, S) CUDA
+        standard normals; otherwise Philox keyed by (seed, global point index m0+m, sample)."""
+        assert self.data_driven_lf_approach, "MC propagation needs a data-driven low-fidelity GP"
+        assert self.augm_iterator.new_entries_count() == 1, "predict_mc supports E = 1 (NARGP)"
+        h = _ffi.get_handle(self.device)
+        self._apply_add_noise()
+        lf, hf = self.lf_model.level_struct(), self.hf_model.level_struct()
+        M, S = int(dX.shape[0]), int(n_samples)
+        mean = torch.empty(M, dtype=torch.float64, device=dX.device)
+        var = torch.empty(M, dtype=torch.float64, device=dX.device)
+        if ws_bytes is None:
+            per_col = (self.hf_model.npad + self.input_dim + 3) * 8
+            want = 16 * M + 148 * 128 * 4 * per_col
+            need = 16 * M + max((S + 256) * per_col, (self.lf_model.npad + 1) * 128 * 8) + 4096
+            ws_bytes = max(min(want, 2 << 30), need)
+        ws = gp.workspace(self.device, ws_bytes)
+        wsum = ctypes.c_double(0.0) if d_weights is not None else None
+        h.check(h.lib.mfgp_predict_mc(
+            h.h, ctypes.byref(lf), ctypes.byref(hf), dX.data_ptr(), M, S,
+            d_eps.data_ptr() if d_eps is not None else None, int(seed), int(m0),
+            int(include_lf_noise), 1, d_weights.data_ptr() if d_weights is not None else None,
+            mean.data_ptr(), var.data_ptr(), ctypes.byref(wsum) if wsum is not None else None,
+            ws.data_ptr(), ws.numel() * 8))
+        return mean, var, (wsum.value if wsum is not None else None)
+
+    def predict_mc(self, X_test, n_samples=100, eps=None, seed=0, weights=None, include_lf_noise=True):
+        """NumPy front end of predict_mc_device.  eps: optional (M, S) or (M, S, 1) standard normals.
+        Returns (mean (M,1), var (M,1)); with `weights` also sets ``self.last_pce_mean``."""
+        assert X_test.ndim == 2 and X_test.shape[1] == self.input_dim
+        d_eps = None
+        if eps is not None:
+            eps = np.asarray(eps, dtype=np.float64).reshape(X_test.shape[0], n_samples)
+            d_eps = gp.to_device(eps, self.device)
+        d_w = gp.to_device(np.asarray(weights).ravel(), self.device) if weights is not None else None
+        mean, var, wsum = self.predict_mc_device(gp.to_device(X_test, self.device), n_samples, d_eps,
+                                                 seed, 0, d_w, include_lf_noise)
+        self.last_pce_mean = wsum
+        return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]
+
+    # -- A9 acquisition (extension) ------------------------------------------------------------------
+    def acquisition_argmax(self, candidates, distributed=False):
+        """(index, variance) of the candidate with the largest predictive variance; lowest index on
+        ties.  With distributed=True every rank scores a contiguous shard and the winners are combined
+        with one all_gather (all ranks must hold the same fitted state, see broadcast_state)."""
+        C = candidates.shape[0]
+        rank, world = dist.rank_world() if distributed else (0, 1)
+        lo, hi = dist.shard_range(C, rank, world)
+        val, idx = -np.inf, -1
+        if hi > lo:
+            dC = gp.to_device(candidates[lo:hi], self.device)
+            _, var = self._predict_device(dC)
+            h = _ffi.get_handle(self.device)
+            c_val, c_idx = ctypes.c_double(), ctypes.c_longlong()
+            h.check(h.lib.mfgp_argmax(h.h, var.data_ptr(), hi - lo, ctypes.byref(c_val), ctypes.byref(c_idx)))
+            val, idx = c_val.value, lo + c_idx.value
+        if distributed and world > 1:
+            val, idx = dist.gather_argmax(val, idx, device="cuda:%d" % self.device)
+        return int(idx), float(val)
+
+    # -- multi-GPU state ------------------------------------------------------------------------------
+    def broadcast_state(self, src=0):
+        """Broadcast the fitted state of both levels from rank `src`: training inputs/targets and
+        hyper-parameters through the object channel, W = L^-1 and alpha as NCCL tensor broadcasts."""
+        import torch.distributed as tdist
+        if not dist.is_dist():
+            return
+        rank = tdist.get_rank()
+        levels = ["hf_model"] + (["lf_model"] if self.data_driven_lf_approach else [])
+        meta = [None]
+        if rank == src:
+            meta[0] = {name: dict(X=getattr(self, name).X, Y=getattr(self, name).Y,
+                                  theta=getattr(self, name).param_array) for name in levels}
+            meta[0]["hf_X"] = self.hf_X
+            meta[0]["kernel"] = self.kernel.param_array.copy()
+        tdist.broadcast_object_list(meta, src=src)
+        m = meta[0]
+        for name in levels:
+            if rank != src:
+                kern = self.kernel if name == "hf_model" else None
+                model = gp.GPRegression(m[name]["X"], m[name]["Y"], kernel=kern)
+                model._set_params(m[name]["theta"])
+                setattr(self, name, model)
+                if name == "hf_model":
+                    self.hf_X, self.hf_Y = m["hf_X"], m[name]["Y"]
+            model = getattr(self, name)
+            if rank == src:
+                model._ensure_posterior()
+            dist.broadcast_tensors([model._dW, model._dalpha], src=src)
+            model._dirty = False

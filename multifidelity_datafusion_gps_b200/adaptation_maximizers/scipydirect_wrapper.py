@@ -1,0 +1,25 @@
+"""DIRECT global search over single-point predicts, as the reference's default maximizer does
+(src/adaptation_maximizers/scipydirect_wrapper.py:16-31).  ``scipydirect`` (Fortran DIRECT) is not
+a dependency of this package; ``scipy.optimize.direct`` is used as a stand-in with scipydirect's
+default budget (maxf=20000, maxT=6000, eps=1e-4).  It is kept for drop-in compatibility of the
+default constructor argument; the GPU-native acquisition is ``CandidateSetMaximizer``."""
+import numpy as np
+
+from .abstract_maximizer import AbstractMaximizer
+
+
+class ScipyDirectMaximizer(AbstractMaximizer):
+    def __init__(self, maxf=20000, maxT=6000, eps=1e-4):
+        super().__init__()
+        self.maxf, self.maxT, self.eps = maxf, maxT, eps
+
+    def maximize(self, model_predict: callable, lower_bound: np.ndarray, upper_bound: np.ndarray):
+        from scipy.optimize import direct
+        bound = [(lower_bound[i], upper_bound[i]) for i in range(len(lower_bound))]
+
+        def acquisition_curve(x):
+            _, uncertainty = model_predict(np.asarray(x)[None])
+            return -float(np.asarray(uncertainty).ravel()[0])
+
+        res = direct(acquisition_curve, bound, eps=self.eps, maxfun=self.maxf, maxiter=self.maxT)
+        return res.x, res.fun

@@ -1,0 +1,258 @@
+// K1 covariance assembly and K5 gradient reduction.
+//
+// K1 replaces kern.K(X) for the reference's two kernels (src/abstractMFGP.py:59-60 and :62-80:
+// RBF(z)*RBF(x) + RBF(x)) plus GPy's diag.add(Ky, noise + 1e-8): one fused pass, no N x N
+// temporaries (GPy materialises three distance matrices and ~6 elementwise temporaries).
+// The product k1*k2 is folded into a single exponential, so a composite element costs two exps.
+// HBM-bound by design: 8 bytes written per element, inputs (N x D) stay in L1/shared memory.
+//
+// K5 replaces GPy's update_gradients_full chain (stationary.py / prod.py / add.py) for
+// dL_dK = 0.5 (alpha alpha^T - K^-1): one streaming pass over K^-1's lower triangle that
+// recomputes the kernel factors from X on the fly and produces six sums
+//   S0 = sum G K12, S1 = sum G K12 rz2, S2 = sum G K12 rx2, S3 = sum G K3, S4 = sum G K3 rx2, S5 = tr G
+// in a fixed order (persistent blocks, fixed tile->block map, two-stage reduction).
+#include "common.cuh"
+
+namespace {
+
+constexpr int AT = 64;   // tile edge
+
+__device__ __forceinline__ void tile_from_linear(int tt, int& ti, int& tj) {
+  ti = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
+  while ((long)(ti + 1) * (ti + 2) / 2 <= tt) ti++;
+  while ((long)ti * (ti + 1) / 2 > tt) ti--;
+  tj = tt - ti * (ti + 1) / 2;
+}
+
+// sX[dd][r] = X[row0 + r][dd] (0 beyond N)
+__device__ __forceinline__ void load_rows(double* sX, const double* X, int N, int D, int row0) {
+  for (int idx = threadIdx.x; idx < AT * D; idx += blockDim.x) {
+    int r = idx / D, dd = idx - r * D;
+    int gr = row0 + r;
+    sX[dd * AT + r] = gr < N ? X[(long)gr * D + dd] : 0.0;
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+    assemble_kernel(KParams kp, const double* __restrict__ X, int N, double diag_add,
+                    double* __restrict__ K, long ldk, int lower_only, int tiles, int nrows) {
+  __shared__ double sXi[MFGP_MAX_D * AT];
+  __shared__ double sXj[MFGP_MAX_D * AT];
+  int ti, tj;
+  if (lower_only) {
+    tile_from_linear(blockIdx.x, ti, tj);
+  } else {
+    ti = blockIdx.x / tiles;
+    tj = blockIdx.x % tiles;
+  }
+  const int row0 = ti * AT, col0 = tj * AT;
+  const int D = kp.D, d = kp.d;
+  load_rows(sXi, X, N, D, row0);
+  load_rows(sXj, X, N, D, col0);
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double rx[4][4], rz[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) rx[i][j] = rz[i][j] = 0.0;
+  for (int dd = 0; dd < D; dd++) {
+    double xi[4], xj[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) xi[i] = sXi[dd * AT + ty + 16 * i];
+#pragma unroll
+    for (int j = 0; j < 4; j++) xj[j] = sXj[dd * AT + 4 * tx + j];
+    if (dd < d) {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double t = xi[i] - xj[j];
+          rx[i][j] = fma(t, t, rx[i][j]);
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double t = xi[i] - xj[j];
+          rz[i][j] = fma(t, t, rz[i][j]);
+        }
+    }
+  }
+  const bool has3 = kp.s3 != 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int r = row0 + ty + 16 * i;
+    if (r >= nrows) continue;
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int c = col0 + 4 * tx + j;
+      double val;
+      if (r < N && c < N) {
+        val = kp.c12 * exp(fma(kp.az, rz[i][j], kp.ax * rx[i][j]));
+        if (has3) val = fma(kp.s3, exp(kp.a3 * rx[i][j]), val);
+        if (r == c) val += diag_add;
+      } else {
+        val = (r == c) ? 1.0 : 0.0;   // identity pad block
+      }
+      v[j] = val;
+    }
+    double* dst = K + (long)r * ldk + col0 + 4 * tx;
+    if (VEC) {
+      // nrows is a multiple of the tile here (padded buffer): no column guard needed
+      reinterpret_cast<double2*>(dst)[0] = make_double2(v[0], v[1]);
+      reinterpret_cast<double2*>(dst)[1] = make_double2(v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (col0 + 4 * tx + j < nrows) dst[j] = v[j];
+    }
+  }
+}
+
+constexpr int GR_BLOCKS = MFGP_NUM_SMS * 4;
+
+__global__ void __launch_bounds__(256)
+    grad_reduce_kernel(KParams kp, const double* __restrict__ X, int N,
+                       const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
+                       int ntiles_lin, double* __restrict__ partials) {
+  __shared__ double sXi[MFGP_MAX_D * AT];
+  __shared__ double sXj[MFGP_MAX_D * AT];
+  __shared__ double sAi[AT], sAj[AT];
+  __shared__ double red[8][6];
+  const int D = kp.D, d = kp.d;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool has3 = kp.s3 != 0.0;
+  double S[6] = {0, 0, 0, 0, 0, 0};
+  for (int tt = blockIdx.x; tt < ntiles_lin; tt += gridDim.x) {
+    int ti, tj;
+    tile_from_linear(tt, ti, tj);
+    const int row0 = ti * AT, col0 = tj * AT;
+    __syncthreads();
+    load_rows(sXi, X, N, D, row0);
+    load_rows(sXj, X, N, D, col0);
+    if (threadIdx.x < AT) {
+      int r = row0 + threadIdx.x;
+      sAi[threadIdx.x] = r < N ? alpha[r] : 0.0;
+    } else if (threadIdx.x < 2 * AT) {
+      int c = col0 + threadIdx.x - AT;
+      sAj[threadIdx.x - AT] = c < N ? alpha[c] : 0.0;
+    }
+    __syncthreads();
+    double rx[4][4], rz[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) rx[i][j] = rz[i][j] = 0.0;
+    for (int dd = 0; dd < D; dd++) {
+      double xi[4], xj[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) xi[i] = sXi[dd * AT + ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) xj[j] = sXj[dd * AT + 4 * tx + j];
+      if (dd < d) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            double t = xi[i] - xj[j];
+            rx[i][j] = fma(t, t, rx[i][j]);
+          }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            double t = xi[i] - xj[j];
+            rz[i][j] = fma(t, t, rz[i][j]);
+          }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int r = row0 + ty + 16 * i;
+      if (r >= N) continue;
+      const double2* src = reinterpret_cast<const double2*>(Kinv + (long)r * ld + col0 + 4 * tx);
+      double2 q0 = src[0], q1 = src[1];
+      double kin[4] = {q0.x, q0.y, q1.x, q1.y};
+      const double ai = sAi[ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c = col0 + 4 * tx + j;
+        if (c > r || c >= N) continue;
+        const double w = (c == r) ? 0.5 : 1.0;   // G = 0.5(aa^T - Kinv); off-diagonal counted twice
+        const double G = w * (ai * sAj[4 * tx + j] - kin[j]);
+        const double k12 = kp.c12 * exp(fma(kp.az, rz[i][j], kp.ax * rx[i][j]));
+        const double gk = G * k12;
+        S[0] += gk;
+        S[1] = fma(gk, rz[i][j], S[1]);
+        S[2] = fma(gk, rx[i][j], S[2]);
+        if (has3) {
+          const double g3 = G * kp.s3 * exp(kp.a3 * rx[i][j]);
+          S[3] += g3;
+          S[4] = fma(g3, rx[i][j], S[4]);
+        }
+        if (c == r) S[5] += G;
+      }
+    }
+  }
+  // block reduction in a fixed order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    double v = S[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = 0.0;
+    for (int w = 0; w < 8; w++) v += red[w][threadIdx.x];
+    partials[blockIdx.x * 8 + threadIdx.x] = v;
+  }
+}
+
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks,
+                                       double* __restrict__ out8) {
+  // 6 warps, one quantity each; lanes stride over blocks, then a shuffle tree: fixed order
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (q >= 6) return;
+  double v = 0.0;
+  for (int b = lane; b < nblocks; b += 32) v += partials[b * 8 + q];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) out8[q] = v;
+}
+
+}  // namespace
+
+int assemble_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, double diag_add,
+                    double* K, long long ldk, int uplo, int npad_identity) {
+  const int nrows = npad_identity > 0 ? npad_identity : N;
+  const int tiles = (nrows + AT - 1) / AT;
+  const int lower = uplo == MFGP_UPLO_LOWER;
+  const int grid = lower ? tiles * (tiles + 1) / 2 : tiles * tiles;
+  const bool vec = (nrows % AT == 0) && (ldk % 2 == 0) && ((uintptr_t)K % 16 == 0);
+  if (vec)
+    assemble_kernel<true><<<grid, 256, 0, h->stream>>>(kp, X, N, diag_add, K, ldk, lower, tiles, nrows);
+  else
+    assemble_kernel<false><<<grid, 256, 0, h->stream>>>(kp, X, N, diag_add, K, ldk, lower, tiles, nrows);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int grad_reduce_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, const double* Kinv,
+                       long long ld, const double* alpha, double* d_out8) {
+  const int tiles = (N + AT - 1) / AT;
+  const int nlin = tiles * (tiles + 1) / 2;
+  const int grid = nlin < GR_BLOCKS ? nlin : GR_BLOCKS;
+  grad_reduce_kernel<<<grid, 256, 0, h->stream>>>(kp, X, N, Kinv, ld, alpha, nlin, h->d_partials);
+  LAUNCH_CHECK(h);
+  reduce_partials_kernel<<<1, 192, 0, h->stream>>>(h->d_partials, grid, d_out8);
+  LAUNCH_CHECK(h);
+  return 0;
+}

@@ -1,0 +1,438 @@
+// extern "C" entry points declared in include/mfgp_b200.h: argument checks, scratch layout,
+// chunk loops and stream ordering.  No torch types, no allocation outside mfgp_create.
+#include "common.cuh"
+
+// launchers defined in predict.cu
+int solve_alpha_launch(mfgp_ctx* h, const double* L, const double* W, int npad, int N,
+                       const double* y, double* v_tmp, double* alpha, double* d_out3);
+int cross_gen_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int npad,
+                     const double* alpha, const double* Xq, long long ncols, long long cols_pad,
+                     double* Ks, double* mean);
+int finish_var_launch(mfgp_ctx* h, const double* ss, long long n, double kdiag, double noise_add,
+                      double* var);
+int build_locs_launch(mfgp_ctx* h, const double* X, long long rows, int d, const double* d_offs,
+                      int E, double tau, double* out);
+int concat_aug_launch(mfgp_ctx* h, const double* X, const double* vals, long long rows, int d, int E,
+                      double* out);
+int fill_normal_launch(mfgp_ctx* h, unsigned long long seed, long long first, long long count,
+                       double* out);
+int build_mc_rows_launch(mfgp_ctx* h, const double* Xtest, const double* mu_l, const double* sd_l,
+                         const double* eps, unsigned long long seed, long long m_global0,
+                         long long m_lo, long long ncols, int S, int d, double* out);
+int sqrt_launch(mfgp_ctx* h, double* v, long long n);
+int mc_aggregate_launch(mfgp_ctx* h, const double* mu_c, const double* v_c, long long npts, int S,
+                        double* mean, double* var);
+int argmax_launch(mfgp_ctx* h, const double* v, long long n, double* d_val, long long* d_idx);
+int wdot_launch(mfgp_ctx* h, const double* w, const double* x, long long n, double* d_out);
+
+#define JITTER_CONST 1e-8   // GPy exact_gaussian_inference.py: diag.add(Ky, variance + 1e-8)
+#define MFGP_SMALL 4096
+
+static char g_err[256] = "invalid handle";
+
+#define ENTER(h)                 \
+  do {                           \
+    if (!(h)) return -1;         \
+    cudaSetDevice((h)->device);  \
+  } while (0)
+
+int make_kparams(mfgp_ctx* h, int kind, int D, int d, const double* theta, int P, KParams* kp) {
+  ARG_CHECK(h, theta != nullptr);
+  ARG_CHECK(h, D >= 1 && D <= MFGP_MAX_D && d >= 1 && d <= D);
+  memset(kp, 0, sizeof(*kp));
+  kp->kind = kind;
+  kp->D = D;
+  kp->d = d;
+  if (kind == MFGP_KIND_COMPOSITE) {
+    ARG_CHECK(h, P == 7 && d < D);
+    for (int i = 0; i < 6; i++) ARG_CHECK(h, theta[i] > 0.0);
+    kp->c12 = theta[0] * theta[2];
+    kp->az = -0.5 / (theta[1] * theta[1]);
+    kp->ax = -0.5 / (theta[3] * theta[3]);
+    kp->s3 = theta[4];
+    kp->a3 = -0.5 / (theta[5] * theta[5]);
+    kp->kdiag = theta[0] * theta[2] + theta[4];
+  } else if (kind == MFGP_KIND_RBF) {
+    ARG_CHECK(h, P == 3);
+    ARG_CHECK(h, theta[0] > 0.0 && theta[1] > 0.0);
+    kp->c12 = theta[0];
+    kp->az = kp->ax = -0.5 / (theta[1] * theta[1]);
+    kp->s3 = 0.0;
+    kp->a3 = 0.0;
+    kp->kdiag = theta[0];
+  } else {
+    ARG_CHECK(h, kind == MFGP_KIND_RBF || kind == MFGP_KIND_COMPOSITE);
+  }
+  ARG_CHECK(h, theta[P - 1] >= 0.0);
+  kp->noise = theta[P - 1];
+  for (int i = 0; i < P; i++) kp->theta[i] = theta[i];
+  return 0;
+}
+
+static int fetch_scalars(mfgp_ctx* h, int ndoubles) {
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_pinned, h->d_scalars, ndoubles * sizeof(double),
+                              cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(h->h_info, h->d_info, 4 * sizeof(int), cudaMemcpyDeviceToHost,
+                              h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" {
+
+int mfgp_version(void) { return 100; }
+
+int mfgp_padded_n(int N) { return round_up(N < 1 ? 1 : N, MFGP_TILE); }
+
+int mfgp_create(int device, mfgp_handle_t* out) {
+  if (!out) return -1;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    snprintf(g_err, sizeof(g_err), "mfgp_create: no CUDA device (this library has no CPU fallback)");
+    return -2;
+  }
+  if (device < 0 || device >= count) {
+    snprintf(g_err, sizeof(g_err), "mfgp_create: device %d out of range (%d devices)", device, count);
+    return -1;
+  }
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "mfgp_create: cannot select device %d", device);
+    return -2;
+  }
+  if (prop.major != 10) {
+    snprintf(g_err, sizeof(g_err), "mfgp_create: device is sm_%d%d; this library is built for sm_100a only",
+             prop.major, prop.minor);
+    return -3;
+  }
+  mfgp_ctx* h = new mfgp_ctx();
+  memset(h, 0, sizeof(*h));
+  h->device = device;
+  h->stream = 0;
+  bool ok = cudaMalloc(&h->d_partials, MFGP_PARTIALS * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&h->d_scalars, MFGP_SMALL * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&h->d_info, 4 * sizeof(int)) == cudaSuccess &&
+            cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) == cudaSuccess &&
+            cudaMallocHost(&h->h_info, 4 * sizeof(int)) == cudaSuccess;
+  for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+  if (ok) ok = cudaMemset(h->d_info, 0, 4 * sizeof(int)) == cudaSuccess;
+  if (!ok || linalg_configure(h) != 0) {
+    snprintf(g_err, sizeof(g_err), "mfgp_create: scratch allocation / kernel configuration failed: %s",
+             cudaGetErrorString(cudaGetLastError()));
+    delete h;
+    return -100;
+  }
+  *out = h;
+  return 0;
+}
+
+int mfgp_destroy(mfgp_handle_t h) {
+  ENTER(h);
+  cudaSetDevice(h->device);
+  cudaFree(h->d_partials);
+  cudaFree(h->d_scalars);
+  cudaFree(h->d_info);
+  cudaFreeHost(h->h_pinned);
+  cudaFreeHost(h->h_info);
+  for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
+  delete h;
+  return 0;
+}
+
+int mfgp_set_stream(mfgp_handle_t h, void* cuda_stream) {
+  ENTER(h);
+  h->stream = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+const char* mfgp_last_error(mfgp_handle_t h) { return h ? h->err : g_err; }
+
+long long mfgp_launch_count(mfgp_handle_t h) { return h ? h->launches : -1; }
+
+int mfgp_assemble(mfgp_handle_t h, int kind, const double* d_X, int N, int D, int d,
+                  const double* h_theta, int P, double jitter, double* d_K, long long ldk, int uplo) {
+  ENTER(h);
+  ARG_CHECK(h, d_X && d_K && N >= 0 && ldk >= N);
+  ARG_CHECK(h, uplo == MFGP_UPLO_LOWER || uplo == MFGP_UPLO_FULL);
+  KParams kp;
+  int rc = make_kparams(h, kind, D, d, h_theta, P, &kp);
+  if (rc) return rc;
+  if (N == 0) return 0;
+  return assemble_launch(h, kp, d_X, N, kp.noise + JITTER_CONST + jitter, d_K, ldk, uplo, 0);
+}
+
+// shared by factorize / lml_grad: returns after enqueueing; scalars at d_scalars[0..2]
+static int factor_enqueue(mfgp_ctx* h, const KParams& kp, const double* d_X, const double* d_y, int N,
+                          double jitter, double* d_A, double* d_W, double* d_alpha,
+                          cudaEvent_t* ev /* optional, 5 events */) {
+  const int npad = mfgp_padded_n(N);
+  ARG_CHECK(h, npad <= MFGP_PARTIALS);
+  int rc;
+  if (ev) CUDA_TRY(h, cudaEventRecord(ev[0], h->stream));
+  if ((rc = assemble_launch(h, kp, d_X, N, kp.noise + JITTER_CONST + jitter, d_A, npad,
+                            MFGP_UPLO_LOWER, npad)))
+    return rc;
+  if (ev) CUDA_TRY(h, cudaEventRecord(ev[1], h->stream));
+  if ((rc = potrf_padded(h, d_A, d_W, npad))) return rc;
+  if (ev) CUDA_TRY(h, cudaEventRecord(ev[2], h->stream));
+  if ((rc = trtri_padded(h, d_A, d_W, npad))) return rc;
+  if (ev) CUDA_TRY(h, cudaEventRecord(ev[3], h->stream));
+  if ((rc = solve_alpha_launch(h, d_A, d_W, npad, N, d_y, h->d_partials, d_alpha, h->d_scalars)))
+    return rc;
+  if (ev) CUDA_TRY(h, cudaEventRecord(ev[4], h->stream));
+  return 0;
+}
+
+int mfgp_factorize(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N, int D,
+                   int d, const double* h_theta, int P, double jitter, double* d_A, double* d_W,
+                   double* d_alpha, double* h_out) {
+  ENTER(h);
+  ARG_CHECK(h, d_X && d_y && d_A && d_W && d_alpha && N >= 1);
+  KParams kp;
+  int rc = make_kparams(h, kind, D, d, h_theta, P, &kp);
+  if (rc) return rc;
+  if ((rc = factor_enqueue(h, kp, d_X, d_y, N, jitter, d_A, d_W, d_alpha, nullptr))) return rc;
+  if ((rc = fetch_scalars(h, 3))) return rc;
+  if (h_out) {
+    h_out[0] = h->h_pinned[0];
+    h_out[1] = h->h_pinned[1];
+    h_out[2] = h->h_pinned[2];
+  }
+  return h->h_info[0];
+}
+
+static void grads_from_sums(const KParams& kp, const double* S, double* g) {
+  const double* th = kp.theta;
+  if (kp.kind == MFGP_KIND_COMPOSITE) {
+    g[0] = S[0] / th[0];
+    g[1] = S[1] / (th[1] * th[1] * th[1]);
+    g[2] = S[0] / th[2];
+    g[3] = S[2] / (th[3] * th[3] * th[3]);
+    g[4] = S[3] / th[4];
+    g[5] = S[4] / (th[5] * th[5] * th[5]);
+    g[6] = S[5];
+  } else {
+    g[0] = S[0] / th[0];
+    g[1] = (S[1] + S[2]) / (th[1] * th[1] * th[1]);
+    g[2] = S[5];
+  }
+}
+
+int mfgp_lml_grad_timed(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N,
+                        int D, int d, const double* h_theta, int P, double jitter, double* d_A,
+                        double* d_W, double* d_alpha, double* h_lml, double* h_grad, double* h_ms) {
+  ENTER(h);
+  ARG_CHECK(h, d_X && d_y && d_A && d_W && d_alpha && N >= 1);
+  KParams kp;
+  int rc = make_kparams(h, kind, D, d, h_theta, P, &kp);
+  if (rc) return rc;
+  const int npad = mfgp_padded_n(N);
+  cudaEvent_t* ev = h_ms ? h->ev : nullptr;
+  if ((rc = factor_enqueue(h, kp, d_X, d_y, N, jitter, d_A, d_W, d_alpha, ev))) return rc;
+  if ((rc = lauum_padded(h, d_W, d_A, npad))) return rc;
+  if (ev) CUDA_TRY(h, cudaEventRecord(ev[5], h->stream));
+  if ((rc = grad_reduce_launch(h, kp, d_X, N, d_A, npad, d_alpha, h->d_scalars + 8))) return rc;
+  if (ev) CUDA_TRY(h, cudaEventRecord(ev[6], h->stream));
+  if ((rc = fetch_scalars(h, 16))) return rc;
+  if (h_lml) h_lml[0] = h->h_pinned[0];
+  if (h_grad) grads_from_sums(kp, h->h_pinned + 8, h_grad);
+  if (h_ms) {
+    for (int i = 0; i < 6; i++) {
+      float ms = 0.f;
+      CUDA_TRY(h, cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      h_ms[i] = ms;
+    }
+  }
+  return h->h_info[0];
+}
+
+int mfgp_lml_grad(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N, int D,
+                  int d, const double* h_theta, int P, double jitter, double* d_A, double* d_W,
+                  double* d_alpha, double* h_lml, double* h_grad) {
+  return mfgp_lml_grad_timed(h, kind, d_X, d_y, N, D, d, h_theta, P, jitter, d_A, d_W, d_alpha,
+                             h_lml, h_grad, nullptr);
+}
+
+int mfgp_potrf(mfgp_handle_t h, double* d_A, double* d_W, int npad) {
+  ENTER(h);
+  ARG_CHECK(h, d_A && d_W);
+  int rc = potrf_padded(h, d_A, d_W, npad);
+  if (rc) return rc;
+  if ((rc = fetch_scalars(h, 1))) return rc;
+  return h->h_info[0];
+}
+
+int mfgp_trtri(mfgp_handle_t h, const double* d_L, double* d_W, int npad) {
+  ENTER(h);
+  ARG_CHECK(h, d_L && d_W);
+  return trtri_padded(h, d_L, d_W, npad);
+}
+
+int mfgp_lauum(mfgp_handle_t h, const double* d_W, double* d_Kinv, int npad) {
+  ENTER(h);
+  ARG_CHECK(h, d_W && d_Kinv && d_W != d_Kinv);
+  return lauum_padded(h, d_W, d_Kinv, npad);
+}
+
+size_t mfgp_predict_ws_bytes(int N, long long cols) {
+  const long long npad = mfgp_padded_n(N);
+  const long long cp = (cols + 127) / 128 * 128;
+  return (size_t)((npad + 1) * cp) * sizeof(double);
+}
+
+static int level_kparams(mfgp_ctx* h, const mfgp_level_t* gp, KParams* kp) {
+  ARG_CHECK(h, gp != nullptr && gp->d_X != nullptr && gp->d_alpha != nullptr && gp->N >= 1);
+  return make_kparams(h, gp->kind, gp->D, gp->d, gp->h_theta, gp->P, kp);
+}
+
+static int predict_impl(mfgp_ctx* h, const mfgp_level_t* gp, const KParams& kp, const double* d_Xnew,
+                        long long M, double* d_mean, double* d_var, int include_noise, double* d_ws,
+                        size_t ws_bytes) {
+  const int npad = mfgp_padded_n(gp->N);
+  int rc;
+  if (M <= 0) return 0;
+  if (!d_var) {   // mean only: no cross-covariance is ever stored
+    ARG_CHECK(h, d_mean != nullptr);
+    return cross_gen_launch(h, kp, gp->d_X, gp->N, npad, gp->d_alpha, d_Xnew, M, M, nullptr, d_mean);
+  }
+  ARG_CHECK(h, gp->d_W != nullptr && d_ws != nullptr);
+  const long long per_col = (long long)npad + 1;
+  long long chunk = (long long)(ws_bytes / sizeof(double)) / per_col / 128 * 128;
+  ARG_CHECK(h, chunk >= 128);
+  double* Ks = d_ws;
+  double* ss = d_ws + chunk * npad;
+  for (long long c0 = 0; c0 < M; c0 += chunk) {
+    const long long ncols = (M - c0 < chunk) ? (M - c0) : chunk;
+    const long long cols_pad = (ncols + 127) / 128 * 128;
+    if ((rc = cross_gen_launch(h, kp, gp->d_X, gp->N, npad, gp->d_alpha, d_Xnew + c0 * kp.D, ncols,
+                               cols_pad, Ks, d_mean ? d_mean + c0 : nullptr)))
+      return rc;
+    if ((rc = trmm_sumsq(h, gp->d_W, npad, Ks, cols_pad, ss))) return rc;
+    if ((rc = finish_var_launch(h, ss, ncols, kp.kdiag, include_noise ? kp.noise : 0.0, d_var + c0)))
+      return rc;
+  }
+  return 0;
+}
+
+int mfgp_predict(mfgp_handle_t h, const mfgp_level_t* gp, const double* d_Xnew, long long M,
+                 double* d_mean, double* d_var, int include_noise, double* d_ws, size_t ws_bytes) {
+  ENTER(h);
+  KParams kp;
+  int rc = level_kparams(h, gp, &kp);
+  if (rc) return rc;
+  ARG_CHECK(h, d_Xnew != nullptr || M == 0);
+  return predict_impl(h, gp, kp, d_Xnew, M, d_mean, d_var, include_noise, d_ws, ws_bytes);
+}
+
+int mfgp_augment(mfgp_handle_t h, const mfgp_level_t* lf, const double* d_X, long long M,
+                 const double* h_offsets, int E, double tau, double* d_Xaug, double* d_ws,
+                 size_t ws_bytes) {
+  ENTER(h);
+  KParams kp;
+  int rc = level_kparams(h, lf, &kp);
+  if (rc) return rc;
+  const int d = lf->D;
+  ARG_CHECK(h, h_offsets && E >= 1 && E <= MFGP_MAX_E && d + E <= MFGP_MAX_D && E * d <= MFGP_SMALL - 64);
+  ARG_CHECK(h, d_X && d_Xaug && d_ws);
+  if (M <= 0) return 0;
+  double* d_offs = h->d_scalars + 64;
+  CUDA_TRY(h, cudaMemcpyAsync(d_offs, h_offsets, (size_t)E * d * sizeof(double),
+                              cudaMemcpyHostToDevice, h->stream));
+  const long long per_row = (long long)E * (d + 1);
+  long long chunk = (long long)(ws_bytes / sizeof(double)) / per_row;
+  ARG_CHECK(h, chunk >= 1);
+  if (chunk > M) chunk = M;
+  double* locs = d_ws;
+  double* vals = d_ws + chunk * E * d;
+  const int npad = mfgp_padded_n(lf->N);
+  for (long long r0 = 0; r0 < M; r0 += chunk) {
+    const long long rows = (M - r0 < chunk) ? (M - r0) : chunk;
+    if ((rc = build_locs_launch(h, d_X + r0 * d, rows, d, d_offs, E, tau, locs))) return rc;
+    if ((rc = cross_gen_launch(h, kp, lf->d_X, lf->N, npad, lf->d_alpha, locs, rows * E, rows * E,
+                               nullptr, vals)))
+      return rc;
+    if ((rc = concat_aug_launch(h, d_X + r0 * d, vals, rows, d, E, d_Xaug + r0 * (d + E)))) return rc;
+  }
+  return 0;
+}
+
+int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
+                    const double* d_Xtest, long long M, int S, const double* d_eps,
+                    unsigned long long seed, long long m0, int include_lf_noise,
+                    int include_hf_noise, const double* d_weights, double* d_mean, double* d_var,
+                    double* h_wsum, double* d_ws, size_t ws_bytes) {
+  ENTER(h);
+  KParams kl, kh;
+  int rc;
+  if ((rc = level_kparams(h, lf, &kl))) return rc;
+  if ((rc = level_kparams(h, hf, &kh))) return rc;
+  const int d = lf->D;
+  ARG_CHECK(h, hf->d == d && hf->D == d + 1);   // E = 1 (NARGP) only
+  ARG_CHECK(h, lf->d_W && hf->d_W && d_Xtest && d_mean && d_var && d_ws && S >= 1 && M >= 0);
+  if (M == 0) return 0;
+  const long long wsd = (long long)(ws_bytes / sizeof(double));
+  ARG_CHECK(h, wsd > 2 * M);
+  double* mu_l = d_ws;
+  double* sd_l = d_ws + M;
+  double* rest = d_ws + 2 * M;
+  const long long restd = wsd - 2 * M;
+  // low-fidelity posterior marginals at the test points
+  if ((rc = predict_impl(h, lf, kl, d_Xtest, M, mu_l, sd_l, include_lf_noise, rest,
+                         (size_t)restd * sizeof(double))))
+    return rc;
+  if ((rc = sqrt_launch(h, sd_l, M))) return rc;
+  // high-fidelity level over (point, sample) columns
+  const int npad = mfgp_padded_n(hf->N);
+  const int D = d + 1;
+  const long long per_col = (long long)npad + D + 2;
+  long long max_cols = restd / per_col / 128 * 128;
+  ARG_CHECK(h, max_cols >= 128);
+  long long pm = max_cols / S;
+  ARG_CHECK(h, pm >= 1);   // the scratch must hold all S samples of at least one point
+  if (pm > M) pm = M;
+  const long long cp_max = (pm * S + 127) / 128 * 128;
+  double* Xq = rest;
+  double* mu_c = Xq + cp_max * D;
+  double* ss = mu_c + cp_max;
+  double* Ks = ss + cp_max;
+  for (long long m_lo = 0; m_lo < M; m_lo += pm) {
+    const long long npts = (M - m_lo < pm) ? (M - m_lo) : pm;
+    const long long ncols = npts * S;
+    const long long cols_pad = (ncols + 127) / 128 * 128;
+    if ((rc = build_mc_rows_launch(h, d_Xtest, mu_l, sd_l, d_eps, seed, m0, m_lo, ncols, S, d, Xq)))
+      return rc;
+    if ((rc = cross_gen_launch(h, kh, hf->d_X, hf->N, npad, hf->d_alpha, Xq, ncols, cols_pad, Ks, mu_c)))
+      return rc;
+    if ((rc = trmm_sumsq(h, hf->d_W, npad, Ks, cols_pad, ss))) return rc;
+    if ((rc = finish_var_launch(h, ss, ncols, kh.kdiag, include_hf_noise ? kh.noise : 0.0, ss)))
+      return rc;
+    if ((rc = mc_aggregate_launch(h, mu_c, ss, npts, S, d_mean + m_lo, d_var + m_lo))) return rc;
+  }
+  if (h_wsum) {
+    if ((rc = wdot_launch(h, d_weights, d_mean, M, h->d_scalars + 20))) return rc;
+    if ((rc = fetch_scalars(h, 24))) return rc;
+    h_wsum[0] += h->h_pinned[20];
+  }
+  return 0;
+}
+
+int mfgp_fill_normal(mfgp_handle_t h, unsigned long long seed, long long first, long long count,
+                     double* d_out) {
+  ENTER(h);
+  ARG_CHECK(h, d_out != nullptr && count >= 0);
+  return fill_normal_launch(h, seed, first, count, d_out);
+}
+
+int mfgp_argmax(mfgp_handle_t h, const double* d_v, long long C, double* h_val, long long* h_idx) {
+  ENTER(h);
+  ARG_CHECK(h, d_v != nullptr && C >= 1 && h_val && h_idx);
+  int rc = argmax_launch(h, d_v, C, h->d_scalars + 16, reinterpret_cast<long long*>(h->d_scalars + 17));
+  if (rc) return rc;
+  if ((rc = fetch_scalars(h, 24))) return rc;
+  h_val[0] = h->h_pinned[16];
+  memcpy(h_idx, h->h_pinned + 17, sizeof(long long));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Shared declarations for the sm_100a kernels behind include/mfgp_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include "../../include/mfgp_b200.h"
+
+#define MFGP_TILE 128            // factor buffers are padded to multiples of this
+#define MFGP_NUM_SMS 148
+
+// Kernel hyper-parameters folded into the coefficients the device code needs.
+//   K(a,b) = c12 * exp(az * |z_a-z_b|^2 + ax * |x_a-x_b|^2) + s3 * exp(a3 * |x_a-x_b|^2)
+// COMPOSITE: c12 = var1*var2, az = -1/(2 len1^2), ax = -1/(2 len2^2), s3 = var3, a3 = -1/(2 len3^2)
+// RBF      : c12 = var, az = ax = -1/(2 len^2), s3 = 0   (x = first d columns, z = the rest)
+struct KParams {
+  int kind, d, D;
+  double c12, az, ax, s3, a3;
+  double kdiag;   // K(a,a)
+  double noise;   // Gaussian_noise.variance
+  double theta[8];
+};
+
+struct mfgp_ctx {
+  int device;
+  cudaStream_t stream;
+  char err[512];
+  long long launches;
+  // fixed scratch (allocated once in mfgp_create)
+  double* d_partials;     // MFGP_PARTIALS doubles: per-block partial sums
+  double* d_scalars;      // 64 doubles: results staged for the host
+  int* d_info;            // 4 ints: [0] first bad pivot (1-based, 0 = ok)
+  double* h_pinned;       // 64 doubles pinned
+  int* h_info;            // 4 ints pinned
+  cudaEvent_t ev[8];
+};
+
+#define MFGP_PARTIALS (1 << 16)
+
+#define CUDA_TRY(h, expr)                                                          \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      snprintf((h)->err, sizeof((h)->err), "%s:%d %s: %s", __FILE__, __LINE__, #expr, \
+               cudaGetErrorString(_e));                                            \
+      return -100;                                                                 \
+    }                                                                              \
+  } while (0)
+
+#define ARG_CHECK(h, cond)                                                         \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      snprintf((h)->err, sizeof((h)->err), "%s:%d bad argument: %s", __FILE__, __LINE__, #cond); \
+      return -1;                                                                   \
+    }                                                                              \
+  } while (0)
+
+#define LAUNCH_CHECK(h)                                                            \
+  do {                                                                             \
+    (h)->launches++;                                                               \
+    cudaError_t _e = cudaGetLastError();                                           \
+    if (_e != cudaSuccess) {                                                       \
+      snprintf((h)->err, sizeof((h)->err), "%s:%d launch: %s", __FILE__, __LINE__, \
+               cudaGetErrorString(_e));                                            \
+      return -101;                                                                 \
+    }                                                                              \
+  } while (0)
+
+static inline int round_up(int n, int m) { return (n + m - 1) / m * m; }
+
+int make_kparams(mfgp_ctx* h, int kind, int D, int d, const double* theta, int P, KParams* kp);
+
+// ---- linalg.cu ---------------------------------------------------------------------------
+int linalg_configure(mfgp_ctx* h);
+int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad);
+int trtri_padded(mfgp_ctx* h, const double* L, double* W, int npad);
+int lauum_padded(mfgp_ctx* h, const double* W, double* Kinv, int npad);
+// tmp = W[:, :]*Ks^T with fused column sum of squares:  out_ss[c] = sum_i (sum_k W[i][k] Ks[c][k])^2
+int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad,
+               double* out_ss);
+
+// ---- assemble.cu -------------------------------------------------------------------------
+int assemble_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, double diag_add,
+                    double* K, long long ldk, int uplo, int npad_identity);
+int grad_reduce_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, const double* Kinv,
+                       long long ld, const double* alpha, double* d_out8);

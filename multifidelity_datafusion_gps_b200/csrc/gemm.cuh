@@ -1,0 +1,234 @@
+// FP64 tensor-pipe GEMM core for sm_100a.
+//
+// tcgen05/UMMA has no FP64 kind, and every mma.sync f64 shape (m8n8k4, m16n8k4/8/16) lowers to
+// DMMA.8x8x4 on sm_100a (checked with cuobjdump), so the FP64 tensor path on B200 is the warp-level
+// DMMA.8x8x4 fed from shared memory.  This core is a 128x128x16 CTA tile, 8 warps of 64x32,
+// 4-stage cp.async (LDGSTS) pipeline, conflict-free padded shared-memory layouts.
+//
+//   C[m][n] (+)= alpha * sum_k A(m,k) * B(n,k)
+//
+// Operand layouts (template flags):
+//   A_KC = true : A(m,k) = A[m*lda + k]   (k contiguous)     false: A(m,k) = A[k*lda + m]
+//   B_KC = true : B(n,k) = B[n*ldb + k]   (k contiguous)     false: B(n,k) = B[k*ldb + n]
+// All extents are multiples of the tile (the factor buffers are padded to 128, see common.cuh), all
+// leading dimensions are even and all base pointers 16-byte aligned, so there is no edge handling.
+#pragma once
+#include "common.cuh"
+
+namespace dg {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
+constexpr int KC_STRIDE = BK + 4;    // [rows][BK] tile, row stride 20 doubles (== 4 mod 16 -> no LDS conflicts)
+constexpr int MC_STRIDE = BM + 4;    // [BK][rows] tile, row stride 132 doubles (== 4 mod 16)
+constexpr int OP_STAGE = BM * KC_STRIDE;              // 2560 doubles >= BK*MC_STRIDE (2112)
+constexpr int STAGE_DOUBLES = 2 * OP_STAGE;
+constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163840
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <bool KC>
+__device__ __forceinline__ void load_operand(double* sdst, const double* g, long ld, int r0, int k0,
+                                             int tid) {
+  if (KC) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int c = tid + i * THREADS;
+      int r = c >> 3, kc = c & 7;
+      cp_async16(sdst + r * KC_STRIDE + kc * 2, g + (long)(r0 + r) * ld + k0 + kc * 2);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int c = tid + i * THREADS;
+      int kr = c >> 6, mc = c & 63;
+      cp_async16(sdst + kr * MC_STRIDE + mc * 2, g + (long)(k0 + kr) * ld + r0 + mc * 2);
+    }
+  }
+}
+
+// acc[i][j][e]: m-tile i (8 rows each), n-tile j (8 cols each); lane holds row g, cols 2t+e.
+template <bool A_KC, bool B_KC>
+__device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* A, long lda,
+                                         const double* B, long ldb, int row0, int col0, int k_begin,
+                                         int k_end, double* smem) {
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int nk = (k_end - k_begin) / BK;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < nk) {
+      double* sa = smem + s * STAGE_DOUBLES;
+      load_operand<A_KC>(sa, A, lda, row0, k_begin + s * BK, tid);
+      load_operand<B_KC>(sa + OP_STAGE, B, ldb, col0, k_begin + s * BK, tid);
+    }
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < nk; kt++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      int nxt = kt + STAGES - 1;
+      if (nxt < nk) {
+        double* sa = smem + (nxt % STAGES) * STAGE_DOUBLES;
+        load_operand<A_KC>(sa, A, lda, row0, k_begin + nxt * BK, tid);
+        load_operand<B_KC>(sa + OP_STAGE, B, ldb, col0, k_begin + nxt * BK, tid);
+      }
+      cp_async_commit();
+    }
+    const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
+    const double* sb = sa + OP_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; kk++) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+        a[i] = A_KC ? sa[(wm0 + 8 * i + g) * KC_STRIDE + kk * 4 + t]
+                    : sa[(kk * 4 + t) * MC_STRIDE + wm0 + 8 * i + g];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        b[j] = B_KC ? sb[(wn0 + 8 * j + g) * KC_STRIDE + kk * 4 + t]
+                    : sb[(kk * 4 + t) * MC_STRIDE + wn0 + 8 * j + g];
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+}
+
+struct GemmParams {
+  const double* A;
+  long lda;
+  const double* B;
+  long ldb;
+  double* C;
+  long ldc;
+  int tiles_m, tiles_n, K;
+  double alpha, beta;
+  int lower_only;                      // enumerate only tiles with ti >= tj (tiles_m == tiles_n)
+  int kb_row, kb_col, ke_row;          // triangular operands: k >= row0 / k >= col0 / k < row0+BM
+};
+
+template <bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmParams p) {
+  extern __shared__ __align__(16) double smem[];
+  int ti, tj;
+  if (p.lower_only) {
+    int tt = blockIdx.x;
+    ti = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
+    while ((long)(ti + 1) * (ti + 2) / 2 <= tt) ti++;
+    while ((long)ti * (ti + 1) / 2 > tt) ti--;
+    tj = tt - ti * (ti + 1) / 2;
+  } else {
+    ti = blockIdx.x / p.tiles_n;
+    tj = blockIdx.x % p.tiles_n;
+  }
+  const int row0 = ti * BM, col0 = tj * BN;
+  int kb = 0, ke = p.K;
+  if (p.kb_row) kb = max(kb, row0);
+  if (p.kb_col) kb = max(kb, col0);
+  if (p.ke_row) ke = min(ke, row0 + BM);
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  if (ke > kb) mainloop<A_KC, B_KC>(acc, p.A, p.lda, p.B, p.ldb, row0, col0, kb, ke, smem);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const long r = row0 + wm0 + 8 * i + g;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      double2* ptr = reinterpret_cast<double2*>(p.C + r * p.ldc + col0 + wn0 + 8 * j + 2 * t);
+      double2 v;
+      v.x = p.alpha * acc[i][j][0];
+      v.y = p.alpha * acc[i][j][1];
+      if (p.beta != 0.0) {
+        double2 o = *ptr;
+        v.x += p.beta * o.x;
+        v.y += p.beta * o.y;
+      }
+      *ptr = v;
+    }
+  }
+}
+
+// tmp = W * Ks^T with fused column sum of squares; one CTA owns a 128-column tile of Ks and walks
+// all row tiles of the lower-triangular W (k < row0+128), so the reduction order is fixed.
+//   out_ss[c] = sum_i ( sum_{k<=i} W[i][k] * Ks[c][k] )^2
+__global__ void __launch_bounds__(THREADS, 1)
+    trmm_sumsq_kernel(const double* W, int npad, const double* Ks, double* out_ss) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double red[2][BN];
+  const int col0 = blockIdx.x * BN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wn0 = (warp & 3) * 32;
+  double ss[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; j++) ss[j][0] = ss[j][1] = 0.0;
+
+  for (int ti = 0; ti < npad / BM; ti++) {
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    mainloop<true, true>(acc, W, npad, Ks, npad, ti * BM, col0, 0, ti * BM + BM, smem);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        ss[j][0] = fma(acc[i][j][0], acc[i][j][0], ss[j][0]);
+        ss[j][1] = fma(acc[i][j][1], acc[i][j][1], ss[j][1]);
+      }
+  }
+  // reduce over the 8 row groups g (lanes with equal t), then over the two warp rows
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      double v = ss[j][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      ss[j][e] = v;
+    }
+  if (g == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      red[warp >> 2][wn0 + 8 * j + 2 * t] = ss[j][0];
+      red[warp >> 2][wn0 + 8 * j + 2 * t + 1] = ss[j][1];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < BN) out_ss[col0 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x];
+}
+
+}  // namespace dg

@@ -1,0 +1,448 @@
+// K6 prediction, K7 Monte-Carlo propagation, K8 acquisition argmax, and the O(N^2) solve kernels.
+//
+// K6 replaces GP.predict -> Posterior._raw_predict (reference src/MFDataFusion.py:156,
+// src/abstractMFGP.py:104): the cross-covariance block is generated on the fly in column chunks
+// (never an N x M matrix in HBM beyond one chunk), the mean is reduced while it is generated, and
+// the variance comes from tmp = W Kx as a DMMA GEMM with a fused column sum-of-squares epilogue.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double kernel_eval(const KParams& kp, const double* __restrict__ q,
+                                              const double* __restrict__ xk) {
+  double rx = 0.0, rz = 0.0;
+  for (int dd = 0; dd < kp.d; dd++) {
+    double t = q[dd] - xk[dd];
+    rx = fma(t, t, rx);
+  }
+  for (int dd = kp.d; dd < kp.D; dd++) {
+    double t = q[dd] - xk[dd];
+    rz = fma(t, t, rz);
+  }
+  double v = kp.c12 * exp(fma(kp.az, rz, kp.ax * rx));
+  if (kp.s3 != 0.0) v = fma(kp.s3, exp(kp.a3 * rx), v);
+  return v;
+}
+
+// One warp per query column c: Ks[c][k] = K(q_c, X_k) for k < N (0 on the pad), mean[c] = Ks[c].alpha
+__global__ void __launch_bounds__(256)
+    cross_gen_kernel(KParams kp, const double* __restrict__ X, int N, int npad,
+                     const double* __restrict__ alpha, const double* __restrict__ Xq,
+                     long long ncols, long long cols_pad, double* __restrict__ Ks,
+                     double* __restrict__ mean) {
+  const int lane = threadIdx.x & 31;
+  const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= cols_pad) return;
+  double* row = Ks ? Ks + c * npad : nullptr;
+  if (c >= ncols) {
+    if (row)
+      for (int k = lane; k < npad; k += 32) row[k] = 0.0;
+    return;
+  }
+  double q[MFGP_MAX_D];
+  for (int dd = 0; dd < kp.D; dd++) q[dd] = Xq[c * kp.D + dd];
+  double acc = 0.0;
+  for (int k = lane; k < npad; k += 32) {
+    double v = 0.0;
+    if (k < N) {
+      v = kernel_eval(kp, q, X + (long)k * kp.D);
+      acc = fma(v, alpha[k], acc);
+    }
+    if (row) row[k] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && mean) mean[c] = acc;
+}
+
+__global__ void finish_var_kernel(const double* ss, long long n, double kdiag, double noise_add,
+                                  double* var) {   // may run in place (ss == var)
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = kdiag - ss[i];
+  v = v < 1e-15 ? 1e-15 : v;   // GPy posterior.py: np.clip(var, 1e-15, inf)
+  var[i] = v + noise_add;
+}
+
+// locations x_i + o_e * tau, row (i*E + e)
+__global__ void build_locs_kernel(const double* __restrict__ X, long long rows, int d,
+                                  const double* __restrict__ offs, int E, double tau,
+                                  double* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = rows * E * d;
+  if (idx >= total) return;
+  int dd = (int)(idx % d);
+  long long re = idx / d;
+  int e = (int)(re % E);
+  long long i = re / E;
+  out[idx] = X[i * d + dd] + offs[e * d + dd] * tau;
+}
+
+// Xaug[i] = [x_i, vals[i*E + 0..E-1]]
+__global__ void concat_aug_kernel(const double* __restrict__ X, const double* __restrict__ vals,
+                                  long long rows, int d, int E, double* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int D = d + E;
+  if (idx >= rows * D) return;
+  long long i = idx / D;
+  int c = (int)(idx - i * D);
+  out[idx] = c < d ? X[i * d + c] : vals[i * E + (c - d)];
+}
+
+// ---- Philox4x32-10 + Box-Muller: one N(0,1) per 64-bit counter --------------------------------
+__device__ __forceinline__ void philox4x32_10(unsigned long long ctr, unsigned long long key,
+                                              unsigned (&out)[4]) {
+  unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = 0u, c3 = 0u;
+  unsigned k0 = (unsigned)key, k1 = (unsigned)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double philox_normal(unsigned long long ctr, unsigned long long seed) {
+  unsigned r[4];
+  philox4x32_10(ctr, seed, r);
+  // two 53-bit-ish uniforms in (0,1)
+  const double u1 = ((double)(((unsigned long long)r[0] << 21) ^ (r[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(((unsigned long long)r[2] << 21) ^ (r[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+  return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+__global__ void fill_normal_kernel(unsigned long long seed, long long first, long long count,
+                                   double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = philox_normal((unsigned long long)(first + i), seed);
+}
+
+// rows [x_m, mu_l[m] + sd_l[m]*eps] for columns c = (m - m_lo)*S + s of the current chunk
+__global__ void build_mc_rows_kernel(const double* __restrict__ Xtest, const double* __restrict__ mu_l,
+                                     const double* __restrict__ sd_l, const double* __restrict__ eps,
+                                     unsigned long long seed, long long m_global0, long long m_lo,
+                                     long long ncols, int S, int d, double* __restrict__ out) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  const long long m = m_lo + c / S;
+  const int s = (int)(c % S);
+  const double e = eps ? eps[m * S + s]
+                       : philox_normal((unsigned long long)((m_global0 + m) * S + s), seed);
+  double* row = out + c * (d + 1);
+  for (int dd = 0; dd < d; dd++) row[dd] = Xtest[m * d + dd];
+  row[d] = fma(sd_l[m], e, mu_l[m]);
+}
+
+__global__ void sqrt_kernel(double* __restrict__ v, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = sqrt(v[i]);
+}
+
+// mean_m = mean_s mu;  var_m = mean_s v + population variance of mu (two-pass, fixed order)
+__global__ void mc_aggregate_kernel(const double* __restrict__ mu_c, const double* __restrict__ v_c,
+                                    long long npts, int S, double* __restrict__ mean,
+                                    double* __restrict__ var) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= npts) return;
+  const double* mu = mu_c + m * S;
+  const double* vv = v_c + m * S;
+  double sm = 0.0, sv = 0.0;
+  for (int s = 0; s < S; s++) {
+    sm += mu[s];
+    sv += vv[s];
+  }
+  const double mbar = sm / S;
+  double dev = 0.0;
+  for (int s = 0; s < S; s++) {
+    double t = mu[s] - mbar;
+    dev = fma(t, t, dev);
+  }
+  mean[m] = mbar;
+  var[m] = sv / S + dev / S;
+}
+
+// ---- deterministic reductions -----------------------------------------------------------------
+constexpr int RED_BLOCKS = 1024;
+
+__global__ void __launch_bounds__(256)
+    argmax_stage1_kernel(const double* __restrict__ v, long long n, double* __restrict__ pval,
+                         long long* __restrict__ pidx) {
+  __shared__ double sv[256];
+  __shared__ long long si[256];
+  double best = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double x = v[i];
+    if (x > best) {   // strictly greater: the lowest index wins (indices ascend per thread)
+      best = x;
+      bi = i;
+    }
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      double x = sv[threadIdx.x + o];
+      long long xi = si[threadIdx.x + o];
+      if (x > sv[threadIdx.x] || (x == sv[threadIdx.x] && xi < si[threadIdx.x])) {
+        sv[threadIdx.x] = x;
+        si[threadIdx.x] = xi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    pval[blockIdx.x] = sv[0];
+    pidx[blockIdx.x] = si[0];
+  }
+}
+
+__global__ void argmax_stage2_kernel(const double* __restrict__ pval, const long long* __restrict__ pidx,
+                                     int nb, double* __restrict__ out_val, long long* __restrict__ out_idx) {
+  __shared__ double sv[256];
+  __shared__ long long si[256];
+  double best = -INFINITY;
+  long long bi = 0x7fffffffffffffffLL;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+    double x = pval[b];
+    long long xi = pidx[b];
+    if (x > best || (x == best && xi < bi)) {
+      best = x;
+      bi = xi;
+    }
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      double x = sv[threadIdx.x + o];
+      long long xi = si[threadIdx.x + o];
+      if (x > sv[threadIdx.x] || (x == sv[threadIdx.x] && xi < si[threadIdx.x])) {
+        sv[threadIdx.x] = x;
+        si[threadIdx.x] = xi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out_val[0] = sv[0];
+    out_idx[0] = si[0];
+  }
+}
+
+// sum_i w[i]*x[i], two deterministic stages
+__global__ void __launch_bounds__(256)
+    wdot_stage1_kernel(const double* __restrict__ w, const double* __restrict__ x, long long n,
+                       double* __restrict__ partials) {
+  __shared__ double sv[256];
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    acc = fma(w ? w[i] : 1.0, x[i], acc);
+  sv[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sv[threadIdx.x] += sv[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = sv[0];
+}
+
+__global__ void sum_stage2_kernel(const double* __restrict__ partials, int nb, double* __restrict__ out) {
+  __shared__ double sv[256];
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) acc += partials[b];
+  sv[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sv[threadIdx.x] += sv[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sv[0];
+}
+
+// ---- O(N^2) solves with the explicit inverse factor W = L^-1 ----------------------------------
+// v[i] = sum_{k<=i} W[i][k] y[k]     (one warp per row)
+__global__ void __launch_bounds__(256)
+    trmv_lower_kernel(const double* __restrict__ W, int npad, const double* __restrict__ y, int N,
+                      double* __restrict__ v) {
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= npad) return;
+  const double* row = W + (long)i * npad;
+  const int kend = min(i + 1, N);
+  double acc = 0.0;
+  for (int k = lane; k < kend; k += 32) acc = fma(row[k], y[k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) v[i] = acc;
+}
+
+// alpha[k] = sum_{i>=k} W[i][k] v[i]; a block owns 32 columns, 8 row lanes, fixed-order reduction
+__global__ void __launch_bounds__(256)
+    trmv_lower_t_kernel(const double* __restrict__ W, int npad, const double* __restrict__ v,
+                        double* __restrict__ alpha) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * 32;
+  const int k = k0 + cx;
+  double a0 = 0.0, a1 = 0.0;
+  int i = k0 + ry;
+  for (; i + 8 < npad; i += 16) {
+    a0 = fma(W[(long)i * npad + k], v[i], a0);
+    a1 = fma(W[(long)(i + 8) * npad + k], v[i + 8], a1);
+  }
+  if (i < npad) a0 = fma(W[(long)i * npad + k], v[i], a0);
+  red[ry][cx] = a0 + a1;
+  __syncthreads();
+  if (ry == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) s += red[r][cx];
+    alpha[k] = s;
+  }
+}
+
+// out[0] = LML, out[1] = logdet, out[2] = y^T alpha     (single block)
+__global__ void __launch_bounds__(256)
+    lml_kernel(const double* __restrict__ L, int npad, int N, const double* __restrict__ y,
+               const double* __restrict__ alpha, double* __restrict__ out) {
+  __shared__ double s0[256], s1[256];
+  double ld = 0.0, ya = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) {
+    ld += log(L[(long)i * npad + i]);
+    ya = fma(y[i], alpha[i], ya);
+  }
+  s0[threadIdx.x] = ld;
+  s1[threadIdx.x] = ya;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s0[threadIdx.x] += s0[threadIdx.x + o];
+      s1[threadIdx.x] += s1[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double logdet = 2.0 * s0[0];
+    out[1] = logdet;
+    out[2] = s1[0];
+    out[0] = 0.5 * (-(double)N * 1.8378770664093453 - logdet - s1[0]);
+  }
+}
+
+inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
+
+}  // namespace
+
+// ---- host launchers ----------------------------------------------------------------------------
+int solve_alpha_launch(mfgp_ctx* h, const double* L, const double* W, int npad, int N,
+                       const double* y, double* v_tmp, double* alpha, double* d_out3) {
+  trmv_lower_kernel<<<nblk(npad, 8), 256, 0, h->stream>>>(W, npad, y, N, v_tmp);
+  LAUNCH_CHECK(h);
+  trmv_lower_t_kernel<<<npad / 32, 256, 0, h->stream>>>(W, npad, v_tmp, alpha);
+  LAUNCH_CHECK(h);
+  lml_kernel<<<1, 256, 0, h->stream>>>(L, npad, N, y, alpha, d_out3);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int cross_gen_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int npad,
+                     const double* alpha, const double* Xq, long long ncols, long long cols_pad,
+                     double* Ks, double* mean) {
+  if (cols_pad <= 0) return 0;
+  cross_gen_kernel<<<nblk(cols_pad, 8), 256, 0, h->stream>>>(kp, X, N, npad, alpha, Xq, ncols,
+                                                             cols_pad, Ks, mean);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int finish_var_launch(mfgp_ctx* h, const double* ss, long long n, double kdiag, double noise_add,
+                      double* var) {
+  if (n <= 0) return 0;
+  finish_var_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(ss, n, kdiag, noise_add, var);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int build_locs_launch(mfgp_ctx* h, const double* X, long long rows, int d, const double* d_offs,
+                      int E, double tau, double* out) {
+  long long total = rows * E * d;
+  if (total <= 0) return 0;
+  build_locs_kernel<<<nblk(total, 256), 256, 0, h->stream>>>(X, rows, d, d_offs, E, tau, out);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int concat_aug_launch(mfgp_ctx* h, const double* X, const double* vals, long long rows, int d, int E,
+                      double* out) {
+  long long total = rows * (d + E);
+  if (total <= 0) return 0;
+  concat_aug_kernel<<<nblk(total, 256), 256, 0, h->stream>>>(X, vals, rows, d, E, out);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int fill_normal_launch(mfgp_ctx* h, unsigned long long seed, long long first, long long count,
+                       double* out) {
+  if (count <= 0) return 0;
+  fill_normal_kernel<<<nblk(count, 256), 256, 0, h->stream>>>(seed, first, count, out);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int build_mc_rows_launch(mfgp_ctx* h, const double* Xtest, const double* mu_l, const double* sd_l,
+                         const double* eps, unsigned long long seed, long long m_global0,
+                         long long m_lo, long long ncols, int S, int d, double* out) {
+  if (ncols <= 0) return 0;
+  build_mc_rows_kernel<<<nblk(ncols, 256), 256, 0, h->stream>>>(Xtest, mu_l, sd_l, eps, seed,
+                                                                m_global0, m_lo, ncols, S, d, out);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int sqrt_launch(mfgp_ctx* h, double* v, long long n) {
+  if (n <= 0) return 0;
+  sqrt_kernel<<<nblk(n, 256), 256, 0, h->stream>>>(v, n);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int mc_aggregate_launch(mfgp_ctx* h, const double* mu_c, const double* v_c, long long npts, int S,
+                        double* mean, double* var) {
+  if (npts <= 0) return 0;
+  mc_aggregate_kernel<<<nblk(npts, 128), 128, 0, h->stream>>>(mu_c, v_c, npts, S, mean, var);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int argmax_launch(mfgp_ctx* h, const double* v, long long n, double* d_val, long long* d_idx) {
+  int nb = (int)((n + 255) / 256);
+  if (nb > RED_BLOCKS) nb = RED_BLOCKS;
+  if (nb < 1) nb = 1;
+  double* pval = h->d_partials;
+  long long* pidx = reinterpret_cast<long long*>(h->d_partials + RED_BLOCKS);
+  argmax_stage1_kernel<<<nb, 256, 0, h->stream>>>(v, n, pval, pidx);
+  LAUNCH_CHECK(h);
+  argmax_stage2_kernel<<<1, 256, 0, h->stream>>>(pval, pidx, nb, d_val, d_idx);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int wdot_launch(mfgp_ctx* h, const double* w, const double* x, long long n, double* d_out) {
+  int nb = (int)((n + 255) / 256);
+  if (nb > RED_BLOCKS) nb = RED_BLOCKS;
+  if (nb < 1) nb = 1;
+  wdot_stage1_kernel<<<nb, 256, 0, h->stream>>>(w, x, n, h->d_partials);
+  LAUNCH_CHECK(h);
+  sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->d_partials, nb, d_out);
+  LAUNCH_CHECK(h);
+  return 0;
+}

@@ -1,0 +1,368 @@
+"""GP engine on the C-ABI: the slice of ``GPy.models.GPRegression`` the reference uses.
+
+The reference delegates all arithmetic to GPy (``src/MFDataFusion.py:93-100``,
+``src/abstractMFGP.py:100-104,131-137``).  This module keeps GPy's *object protocol* for that
+slice -- ``GPRegression(X, Y, kernel)``, ``model['.*Gaussian_noise']`` with ``fix / unfix /
+constrain_positive``, ``optimize``, ``optimize_restarts``, ``predict``, ``likelihood.variance``,
+``Y`` -- and routes every numerical step (covariance assembly, Cholesky, solves, LML, gradient,
+prediction) to the sm_100a kernels behind ``include/mfgp_b200.h``.  The optimiser itself is
+SciPy's L-BFGS-B on the host, exactly as paramz does it; its objective is one GPU evaluation.
+
+No CPU fallback: constructing a model without a visible B200 raises ``MfgpError``.
+"""
+import ctypes
+import re
+
+import numpy as np
+import torch
+from scipy import optimize as _sopt
+
+from . import _ffi
+from ._ffi import KIND_COMPOSITE, KIND_RBF, MfgpError, NotPositiveDefinite, padded_n
+
+_LIM_VAL = 36.0
+_LOG_LIM_VAL = float(np.log(np.finfo(np.float64).max))
+
+
+# -- paramz Logexp transformation (paramz/transformations.py) --------------------------------
+def logexp_f(x):
+    x = np.asarray(x, dtype=np.float64)
+    return np.where(x > _LIM_VAL, x, np.log1p(np.exp(np.clip(x, -_LOG_LIM_VAL, _LIM_VAL))))
+
+
+def logexp_finv(f):
+    f = np.asarray(f, dtype=np.float64)
+    with np.errstate(over="ignore"):
+        return np.where(f > _LIM_VAL, f, np.log(np.expm1(f)))
+
+
+def logexp_gradfactor(f):
+    f = np.asarray(f, dtype=np.float64)
+    return np.where(f > _LIM_VAL, 1.0, -np.expm1(-f))
+
+
+# -- kernels --------------------------------------------------------------------------------
+class Kernel:
+    """Kernel object with persistent hyper-parameters (the reference re-uses ONE kernel object
+    across fits, ``src/MFDataFusion.py:96``, so every fit warm-starts from the previous optimum)."""
+
+    def __init__(self, kind, input_dim, d, names):
+        self.kind = kind
+        self.input_dim = int(input_dim)     # D: all columns
+        self.d = int(d)                     # leading plain-input columns
+        self.names = list(names)
+        self.param_array = np.ones(len(names), dtype=np.float64)   # GPy defaults: all 1.0
+
+    def to_dict(self):
+        p = self.param_array
+        if self.kind == KIND_RBF:
+            return {"class": "RBF", "variance": [p[0]], "lengthscale": [p[1]]}
+        rbf = lambda i: {"class": "RBF", "variance": [p[i]], "lengthscale": [p[i + 1]]}
+        return {"class": "Add", "parts": {0: {"class": "Prod", "parts": {0: rbf(0), 1: rbf(2)}},
+                                          1: rbf(4)}}
+
+
+def RBF(input_dim):
+    """GPy.kern.RBF(input_dim) (non-ARD: one lengthscale; src/abstractMFGP.py:60)."""
+    return Kernel(KIND_RBF, input_dim, input_dim, ["rbf.variance", "rbf.lengthscale"])
+
+
+def NARGPKernel(input_dim, aug_dim):
+    """RBF(aug dims) * RBF(x dims) + RBF(x dims) (src/abstractMFGP.py:62-80)."""
+    return Kernel(KIND_COMPOSITE, input_dim + aug_dim, input_dim,
+                  ["sum.mul.rbf.variance", "sum.mul.rbf.lengthscale",
+                   "sum.mul.rbf_1.variance", "sum.mul.rbf_1.lengthscale",
+                   "sum.rbf.variance", "sum.rbf.lengthscale"])
+
+
+class _Likelihood:
+    def __init__(self, model):
+        self._m = model
+
+    @property
+    def variance(self):
+        return self._m._noise
+
+    @variance.setter
+    def variance(self, v):   # GPy: assignment triggers parameters_changed -> re-inference
+        self._m._noise = float(np.asarray(v).ravel()[0])
+        self._m._dirty = True
+
+
+class _ParamView:
+    """Result of ``model[regex]``: supports fix / unfix / constrain_positive / value access."""
+
+    def __init__(self, model, idx):
+        self._m, self._idx = model, idx
+
+    def fix(self):
+        self._m._fixed[self._idx] = True
+
+    def unfix(self):
+        self._m._fixed[self._idx] = False
+
+    def constrain_positive(self):
+        pass   # every parameter of this model is Logexp-constrained already
+
+    @property
+    def values(self):
+        return self._m.param_array[self._idx]
+
+
+def current_device():
+    """torch's current CUDA device; raises MfgpError when there is none (no CPU fallback)."""
+    if not torch.cuda.is_available():
+        raise MfgpError("no CUDA device visible: mfgp_b200 runs on B200 only and has no CPU fallback")
+    return torch.cuda.current_device()
+
+
+_ws_pool = {}
+
+
+def workspace(device, nbytes):
+    """Grow-only scratch tensor per device (caller-owned scratch of the C-ABI calls)."""
+    key = int(device)
+    n = (int(nbytes) + 7) // 8
+    cur = _ws_pool.get(key)
+    if cur is None or cur.numel() < n:
+        _ws_pool[key] = None
+        cur = torch.empty(n, dtype=torch.float64, device="cuda:%d" % key)
+        _ws_pool[key] = cur
+    return cur
+
+
+def to_device(arr, device):
+    """numpy (host) -> contiguous float64 CUDA tensor through pinned memory."""
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    t = torch.from_numpy(a)
+    if a.size >= 1 << 16:
+        t = t.pin_memory()
+    return t.to("cuda:%d" % device, non_blocking=False)
+
+
+class GPRegression:
+    """GPy.models.GPRegression look-alike running on one B200."""
+
+    def __init__(self, X, Y, kernel=None, initialize=True, device=None):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        assert X.ndim == 2 and Y.ndim == 2 and Y.shape == (X.shape[0], 1)
+        if kernel is None:
+            kernel = RBF(X.shape[1])                       # GPRegression default kernel
+        assert kernel.input_dim == X.shape[1], "kernel/input dimension mismatch"
+        self.device = current_device() if device is None else int(device)
+        self._handle = _ffi.get_handle(self.device)        # raises without a GPU / library
+        self.X, self.Y = X, Y
+        self.kern = kernel
+        self._noise = 1.0                                   # Gaussian likelihood default
+        self.likelihood = _Likelihood(self)
+        self.N, self.D = X.shape
+        self.npad = padded_n(self.N)
+        dev = "cuda:%d" % self.device
+        self._dX = to_device(X, self.device)
+        self._dy = to_device(Y.ravel(), self.device)
+        self._dA = torch.empty((self.npad, self.npad), dtype=torch.float64, device=dev)
+        self._dW = torch.empty((self.npad, self.npad), dtype=torch.float64, device=dev)
+        self._dalpha = torch.empty(self.npad, dtype=torch.float64, device=dev)
+        self._fixed = np.zeros(len(kernel.names) + 1, dtype=bool)
+        self._dirty = True
+        self._fail_count = 0
+        self.n_evals = 0
+        self.optimization_runs = []
+        self._theta_c = (ctypes.c_double * 8)()
+        self.last_jitter = 0.0
+
+    # -- parameters ------------------------------------------------------------------------
+    @property
+    def names(self):
+        return self.kern.names + ["Gaussian_noise.variance"]
+
+    @property
+    def param_array(self):
+        return np.concatenate([self.kern.param_array, [self._noise]])
+
+    def _set_params(self, theta):
+        self.kern.param_array[:] = theta[:-1]
+        self._noise = float(theta[-1])
+        self._dirty = True
+
+    def _match(self, pattern):
+        rx = re.compile(pattern)
+        idx = np.array([bool(rx.match(n)) for n in self.names])
+        if not idx.any():
+            raise KeyError(pattern)
+        return idx
+
+    def __getitem__(self, pattern):
+        return _ParamView(self, self._match(pattern))
+
+    def __setitem__(self, pattern, value):
+        theta = self.param_array
+        theta[self._match(pattern)] = float(np.asarray(value).ravel()[0])
+        self._set_params(theta)
+
+    # -- inference on the GPU ----------------------------------------------------------------
+    def _theta_ptr(self, theta):
+        for i, v in enumerate(theta):
+            self._theta_c[i] = float(v)
+        return ctypes.cast(self._theta_c, ctypes.c_void_p)
+
+    def _jitter_schedule(self, theta):
+        """GPy.util.linalg.jitchol: first try without jitter, then mean(diag)*1e-6*10^k, k<5."""
+        kdiag = theta[0] * theta[2] + theta[4] if self.kern.kind == KIND_COMPOSITE else theta[0]
+        base = (kdiag + theta[-1] + 1e-8) * 1e-6
+        return [0.0] + [base * 10.0 ** k for k in range(5)]
+
+    def _call_with_jitter(self, fn, theta):
+        last = None
+        for jit in self._jitter_schedule(theta):
+            rc = fn(jit)
+            if rc == 0:
+                self.last_jitter = jit
+                return
+            if rc < 0:
+                self._handle.check(rc)
+            last = rc
+        raise NotPositiveDefinite(last)
+
+    def lml_and_grad(self, theta=None, timings=None):
+        """One LML + gradient evaluation (untransformed space).  Leaves the posterior
+        (W = L^-1, alpha) of ``theta`` in place."""
+        h = _ffi.get_handle(self.device)
+        theta = self.param_array if theta is None else np.asarray(theta, dtype=np.float64)
+        P = len(theta)
+        lml = ctypes.c_double()
+        grad = (ctypes.c_double * 8)()
+        ms = (ctypes.c_double * 8)() if timings is not None else None
+        tp = self._theta_ptr(theta)
+
+        def run(jit):
+            return h.lib.mfgp_lml_grad_timed(
+                h.h, self.kern.kind, self._dX.data_ptr(), self._dy.data_ptr(), self.N, self.D,
+                self.kern.d, tp, P, jit, self._dA.data_ptr(), self._dW.data_ptr(),
+                self._dalpha.data_ptr(), ctypes.byref(lml), ctypes.cast(grad, ctypes.c_void_p),
+                ctypes.cast(ms, ctypes.c_void_p) if ms is not None else None)
+
+        self._call_with_jitter(run, theta)
+        self.n_evals += 1
+        if timings is not None:
+            timings[:] = [ms[i] for i in range(6)]
+        self._post_theta = theta.copy()
+        self._dirty = not np.array_equal(theta, self.param_array)
+        return lml.value, np.array([grad[i] for i in range(P)])
+
+    def _ensure_posterior(self):
+        if not self._dirty:
+            return
+        h = _ffi.get_handle(self.device)
+        theta = self.param_array
+        out = (ctypes.c_double * 3)()
+        tp = self._theta_ptr(theta)
+
+        def run(jit):
+            return h.lib.mfgp_factorize(
+                h.h, self.kern.kind, self._dX.data_ptr(), self._dy.data_ptr(), self.N, self.D,
+                self.kern.d, tp, len(theta), jit, self._dA.data_ptr(), self._dW.data_ptr(),
+                self._dalpha.data_ptr(), ctypes.cast(out, ctypes.c_void_p))
+
+        self._call_with_jitter(run, theta)
+        self._lml = out[0]
+        self._dirty = False
+
+    def log_likelihood(self):
+        self._dirty = True
+        self._ensure_posterior()
+        return self._lml
+
+    # -- paramz optimisation -----------------------------------------------------------------
+    def _objective_grads(self, x):
+        """paramz Model._objective_grads over the transformed, un-fixed parameters."""
+        free = ~self._fixed
+        theta = self.param_array
+        theta[free] = logexp_f(x)
+        self._set_params(theta)
+        try:
+            lml, g = self.lml_and_grad(theta)
+            self._fail_count = 0
+        except NotPositiveDefinite:
+            if self._fail_count >= 10:
+                raise
+            self._fail_count += 1
+            return np.inf, np.zeros(int(free.sum()))
+        return -lml, -(g[free] * logexp_gradfactor(theta[free]))
+
+    def optimize(self, optimizer=None, max_iters=1000, messages=False, **kw):
+        free = ~self._fixed
+        x0 = logexp_finv(self.param_array[free])
+        x_opt, f_opt, _ = _sopt.fmin_l_bfgs_b(self._objective_grads, x0, maxfun=max_iters,
+                                               maxiter=max_iters)
+        theta = self.param_array
+        theta[free] = logexp_f(x_opt)
+        self._set_params(theta)
+        self.optimization_runs.append((x_opt, float(f_opt)))
+        return self
+
+    def optimize_restarts(self, num_restarts=10, robust=False, verbose=True, parallel=False,
+                          num_processes=None, **kwargs):
+        """paramz Model.optimize_restarts: run 0 from the current point, runs 1.. from N(0,1) draws
+        in the transformed space (global NumPy RNG), keep the best objective."""
+        free = ~self._fixed
+        kwargs.pop("optimizer", None)      # 'bfgs' resolves to L-BFGS-B in paramz.get_optimizer
+        first = len(self.optimization_runs)
+        for i in range(num_restarts):
+            try:
+                if i > 0:
+                    theta = self.param_array
+                    theta[free] = logexp_f(np.random.normal(size=int(free.sum())))
+                    self._set_params(theta)
+                self.optimize(**kwargs)
+            except Exception:
+                if robust:
+                    continue
+                raise
+        runs = self.optimization_runs[first:]
+        if runs:
+            best = int(np.argmin([r[1] for r in runs]))
+            theta = self.param_array
+            theta[free] = logexp_f(runs[best][0])
+            self._set_params(theta)
+        return self
+
+    # -- prediction ----------------------------------------------------------------------------
+    def level_struct(self):
+        """mfgp_level_t view of the fitted state (keeps the ctypes theta buffer alive on self)."""
+        self._ensure_posterior()
+        theta = self.param_array
+        self._level_theta = (ctypes.c_double * 8)(*theta)
+        return _ffi.Level(kind=self.kern.kind, N=self.N, D=self.D, d=self.kern.d, P=len(theta),
+                          reserved=0, d_X=self._dX.data_ptr(),
+                          h_theta=ctypes.cast(self._level_theta, ctypes.c_void_p).value,
+                          d_W=self._dW.data_ptr(), d_alpha=self._dalpha.data_ptr())
+
+    def predict_device(self, dXnew, want_var=True, include_noise=True, ws_bytes=None):
+        """dXnew: (M, D) CUDA float64 tensor -> (mean (M,), var (M,) or None) CUDA tensors."""
+        h = _ffi.get_handle(self.device)
+        lvl = self.level_struct()
+        M = int(dXnew.shape[0])
+        dev = dXnew.device
+        mean = torch.empty(M, dtype=torch.float64, device=dev)
+        var = torch.empty(M, dtype=torch.float64, device=dev) if want_var else None
+        ws_ptr, nbytes = None, 0
+        if want_var:
+            if ws_bytes is None:
+                ws_bytes = min(h.lib.mfgp_predict_ws_bytes(self.N, max(M, 1)), 1 << 30)
+                ws_bytes = max(ws_bytes, h.lib.mfgp_predict_ws_bytes(self.N, 128))
+            ws = workspace(self.device, ws_bytes)
+            ws_ptr, nbytes = ws.data_ptr(), ws.numel() * 8
+        h.check(h.lib.mfgp_predict(h.h, ctypes.byref(lvl), dXnew.data_ptr(), M, mean.data_ptr(),
+                                   var.data_ptr() if want_var else None, int(include_noise),
+                                   ws_ptr, nbytes))
+        return mean, var
+
+    def predict(self, Xnew, full_cov=False, include_likelihood=True):
+        """GP.predict: (mean (M,1), var (M,1)) as NumPy; var includes the noise variance."""
+        assert not full_cov, "full_cov is not on the reference's path"
+        Xnew = np.ascontiguousarray(Xnew, dtype=np.float64)
+        assert Xnew.ndim == 2 and Xnew.shape[1] == self.D
+        mean, var = self.predict_device(to_device(Xnew, self.device), True, include_likelihood)
+        return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]

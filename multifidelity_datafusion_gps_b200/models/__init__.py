@@ -1,0 +1,3 @@
+from .GPDF import GPDF
+from .GPDFC import GPDFC
+from .NARGP import NARGP

@@ -1,0 +1,221 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): predictive mean 1e-8 relative, variance and LML 1e-6 relative,
+arg-max index bit-exact.  The CUDA kernels compute distances as sum (x-y)^2; the oracle offers that
+form ("direct", tight bound) and GPy's expansion form ("gpy", the parity bound)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from oracle import gpy_oracle as go
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T(gpu):
+    import torch
+    from multifidelity_datafusion_gps_b200 import ops
+
+    class NS:
+        pass
+    ns = NS()
+    ns.torch, ns.ops = torch, ops
+    ns.dev = "cuda:0"
+    ns.up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to("cuda:0")
+    return ns
+
+
+CASES = [(go.KIND_COMPOSITE, 1, 1), (go.KIND_COMPOSITE, 2, 5), (go.KIND_COMPOSITE, 4, 1),
+         (go.KIND_RBF, 2, 5), (go.KIND_RBF, 3, 0)]
+
+
+@pytest.mark.parametrize("kind,d,E", CASES)
+@pytest.mark.parametrize("N", [1, 7, 64, 65, 200, 333])
+def test_assemble_matches_oracle(T, kind, d, E, N):
+    X, _, th = util.random_case(N, N, d, E, kind)
+    for uplo in (0, 1):
+        K = T.ops.assemble(T.up(X), kind, d, th, uplo=uplo).cpu().numpy()
+        ref_d = go.assemble_Ky(kind, X, d, th, form="direct")
+        ref_g = go.assemble_Ky(kind, X, d, th, form="gpy")
+        if uplo == 0:
+            K, ref_d, ref_g = np.tril(K), np.tril(ref_d), np.tril(ref_g)
+        assert util.rel_err(K, ref_d) < 5e-15
+        assert util.rel_err(K, ref_g) < 1e-11
+
+
+def test_assemble_odd_leading_dimension_and_jitter(T):
+    X, _, th = util.random_case(1, 37, 2, 5, go.KIND_COMPOSITE)
+    K = T.ops.assemble(T.up(X), go.KIND_COMPOSITE, 2, th, uplo=1, jitter=0.25, ld=41).cpu().numpy()
+    ref = go.assemble_Ky(go.KIND_COMPOSITE, X, 2, th, form="direct") + 0.25 * np.eye(37)
+    assert util.rel_err(K[:, :37], ref) < 5e-15
+    assert np.all(K[:, 37:] == 0.0)
+
+
+@pytest.mark.parametrize("n", [128, 200, 256, 384, 640, 1000])
+def test_potrf_trtri_lauum_match_lapack(T, n):
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n))
+    A = B @ B.T / n + np.eye(n)
+    Ap = T.ops.pad_spd(T.up(A))
+    W, info = T.ops.potrf(Ap)
+    assert info == 0
+    L = np.tril(Ap.cpu().numpy())[:n, :n]
+    Lref = sla.cholesky(A, lower=True)
+    assert util.rel_err(L, Lref) < 1e-12
+    T.ops.trtri(Ap, W)
+    Wn = np.tril(W.cpu().numpy())
+    assert util.rel_err(Wn[:n, :n], np.linalg.inv(Lref)) < 1e-11
+    assert np.allclose(Wn[n:, n:], np.eye(Wn.shape[0] - n))      # identity pad survives
+    Kinv = np.tril(T.ops.lauum(W).cpu().numpy())[:n, :n]
+    assert util.rel_err(Kinv, np.tril(np.linalg.inv(A))) < 1e-11
+
+
+def test_potrf_reports_first_bad_pivot(T):
+    n = 300
+    A = np.eye(n)
+    A[170, 170] = -1.0
+    Ap = T.ops.pad_spd(T.up(A))
+    _, info = T.ops.potrf(Ap)
+    assert info == 171          # LAPACK convention: 1-based index of the failing pivot
+
+
+@pytest.mark.parametrize("kind,d,E", CASES)
+@pytest.mark.parametrize("N", [1, 10, 30, 200, 700])
+def test_lml_and_gradient_match_oracle(T, kind, d, E, N):
+    X, Y, th = util.random_case(100 + N, N, d, E, kind)
+    buf = T.ops.FactorBuffers(N, T.dev)
+    lml, g, info = T.ops.lml_grad(T.up(X), T.up(Y.ravel()), kind, d, th, buf)
+    assert info == 0
+    for form, tol in (("direct", 1e-9), ("gpy", 1e-6)):
+        ref = go.inference(kind, X, Y, d, th, form=form)
+        assert abs(lml - ref["lml"]) <= tol * abs(ref["lml"])
+        assert util.rel_err(g, ref["grad"]) < max(tol, 1e-8)
+        assert util.rel_err(buf.alpha.cpu().numpy()[:N], ref["alpha"].ravel()) < max(tol, 1e-8)
+        Ki = np.tril(buf.A.cpu().numpy())[:N, :N]
+        assert util.rel_err(Ki, np.tril(ref["Ki"])) < max(tol, 1e-8)
+
+
+@pytest.mark.parametrize("kind,d,E", CASES)
+def test_factorize_and_predict_match_oracle(T, kind, d, E):
+    N, M = 150, 777
+    X, Y, th = util.random_case(7, N, d, E, kind)
+    Xs = np.random.default_rng(8).uniform(size=(M, d + E))
+    Xs[:5] = X[:5]                                      # test points on training points: tiny variance
+    buf = T.ops.FactorBuffers(N, T.dev)
+    dX = T.up(X)
+    lml, logdet, yta, info = T.ops.factorize(dX, T.up(Y.ravel()), kind, d, th, buf)
+    assert info == 0
+    ref = go.inference(kind, X, Y, d, th, form="gpy", want_grad=False)
+    assert abs(lml - ref["lml"]) <= 1e-6 * abs(ref["lml"])
+    lvl = T.ops.LevelRef(dX, kind, d, th, buf)
+    for include_noise in (True, False):
+        mean, var = T.ops.predict(lvl, T.up(Xs), True, include_noise)
+        mu_ref, var_ref = go.posterior_predict(kind, X, d, th, ref["L"], ref["alpha"], Xs, include_noise)
+        scale = np.max(np.abs(mu_ref))
+        assert util.rel_err(mean.cpu().numpy(), mu_ref.ravel(), scale) < 1e-8
+        kdiag = go.kernel_Kdiag(kind, th[:-1], 1)[0]
+        assert util.rel_err(var.cpu().numpy(), var_ref.ravel(), kdiag) < 1e-6
+    mean_only, none = T.ops.predict(lvl, T.up(Xs), want_var=False)
+    assert none is None and T.torch.equal(mean_only, mean)
+
+
+def test_predict_chunking_is_bit_invariant(T):
+    # the chunk size of the cross-covariance scratch must not change a single bit of the outputs
+    kind, d, E, N, M = go.KIND_COMPOSITE, 2, 5, 300, 1000
+    X, Y, th = util.random_case(9, N, d, E, kind)
+    Xs = np.random.default_rng(10).uniform(size=(M, d + E))
+    buf = T.ops.FactorBuffers(N, T.dev)
+    dX = T.up(X)
+    T.ops.factorize(dX, T.up(Y.ravel()), kind, d, th, buf)
+    lvl = T.ops.LevelRef(dX, kind, d, th, buf)
+    from multifidelity_datafusion_gps_b200 import _ffi
+    h = _ffi.get_handle(0)
+    m1, v1 = T.ops.predict(lvl, T.up(Xs))
+    m2, v2 = T.ops.predict(lvl, T.up(Xs), ws_bytes=h.lib.mfgp_predict_ws_bytes(N, 128))
+    assert T.torch.equal(m1, m2) and T.torch.equal(v1, v2)
+    m3, v3 = T.ops.predict(lvl, T.up(Xs[500:]))
+    assert T.torch.equal(m1[500:], m3) and T.torch.equal(v1[500:], v3)
+
+
+def test_empty_inputs(T):
+    kind, d, E, N = go.KIND_RBF, 2, 0, 20
+    X, Y, th = util.random_case(11, N, d, E, kind)
+    buf = T.ops.FactorBuffers(N, T.dev)
+    dX = T.up(X)
+    T.ops.factorize(dX, T.up(Y.ravel()), kind, d, th, buf)
+    lvl = T.ops.LevelRef(dX, kind, d, th, buf)
+    mean, var = T.ops.predict(lvl, T.torch.empty((0, d), dtype=T.torch.float64, device=T.dev))
+    assert mean.numel() == 0 and var.numel() == 0
+
+
+def test_argmax_matches_numpy_including_ties(T):
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 257, 100000, 1 << 20):
+        v = rng.standard_normal(n)
+        if n > 4:
+            v[[n // 3, n // 2, n - 1]] = v.max() + 1.0          # three-way tie: lowest index wins
+        val, idx = T.ops.argmax(T.up(v))
+        assert idx == int(np.argmax(v)) and val == v[idx]
+
+
+def test_philox_normals_are_standard_and_counter_based(T):
+    a = T.ops.fill_normal(2, 0, 1 << 20, T.dev)
+    b = T.ops.fill_normal(2, 1000, 4096, T.dev)
+    assert T.torch.equal(a[1000:1000 + 4096], b)        # value depends on (seed, counter) only
+    x = a.cpu().numpy()
+    assert abs(x.mean()) < 5e-3 and abs(x.var() - 1.0) < 5e-3
+    assert abs(np.mean(x ** 3)) < 2e-2 and abs(np.mean(x ** 4) - 3.0) < 5e-2
+    c = T.ops.fill_normal(3, 0, 4096, T.dev)
+    assert not T.torch.equal(a[:4096], c)
+
+
+def test_bad_arguments_are_rejected(T):
+    from multifidelity_datafusion_gps_b200 import _ffi
+    X, _, th = util.random_case(1, 10, 2, 5, go.KIND_COMPOSITE)
+    with pytest.raises(_ffi.MfgpError):
+        T.ops.assemble(T.up(X), go.KIND_COMPOSITE, 2, th[:3])            # wrong P
+    bad = th.copy()
+    bad[1] = -1.0
+    with pytest.raises(_ffi.MfgpError):
+        T.ops.assemble(T.up(X), go.KIND_COMPOSITE, 2, bad)               # negative lengthscale
+
+
+def test_large_factorization_properties(T):
+    # size-independent properties at a size the oracle would take minutes for:
+    # W L = I, K^-1 K_y = I (sampled columns), LML consistent with logdet/quadratic form
+    kind, d, E, N = go.KIND_COMPOSITE, 4, 1, 4096
+    rng = np.random.default_rng(1)
+    X = rng.uniform(size=(N, d + E))
+    Y = util.hf_4d(X[:, :4])
+    th = np.array([1.0, 0.3, 1.0, 0.3, 0.1, 0.3, 0.01 * Y.var()])
+    dX, dy = T.up(X), T.up(Y.ravel())
+    buf = T.ops.FactorBuffers(N, T.dev)
+    lml, logdet, yta, info = T.ops.factorize(dX, dy, kind, d, th, buf)
+    assert info == 0
+    torch = T.torch
+    L = torch.tril(buf.A)
+    W = torch.tril(buf.W)
+    I = torch.eye(buf.npad, dtype=torch.float64, device=T.dev)
+    assert (W @ L - I).abs().max().item() < 1e-9
+    Ky = T.ops.assemble(dX, kind, d, th, uplo=1)
+    assert ((L[:N, :N] @ L[:N, :N].T) - Ky).abs().max().item() < 1e-11
+    assert (Ky @ buf.alpha[:N] - dy).abs().max().item() < 1e-8 * Y.max()
+    assert abs(lml - 0.5 * (-N * np.log(2 * np.pi) - logdet - yta)) < 1e-9 * abs(lml)
+    lml2, g, info = T.ops.lml_grad(dX, dy, kind, d, th, buf)
+    assert info == 0 and abs(lml2 - lml) <= 1e-12 * abs(lml)
+    Ki = torch.tril(buf.A) + torch.tril(buf.A, -1).T
+    cols = torch.arange(0, N, 97, device=T.dev)
+    R = Ki[:N, :N] @ Ky[:, cols]
+    assert (R - I[:N, cols]).abs().max().item() < 1e-7
+    # gradient against central finite differences of the GPU LML itself
+    for i in (1, 3, 6):
+        hstep = 1e-5 * th[i]
+        tp, tm = th.copy(), th.copy()
+        tp[i] += hstep
+        tm[i] -= hstep
+        lp = T.ops.factorize(dX, dy, kind, d, tp, buf)[0]
+        lm = T.ops.factorize(dX, dy, kind, d, tm, buf)[0]
+        fd = (lp - lm) / (2 * hstep)
+        assert abs(g[i] - fd) <= 1e-5 * max(1.0, abs(fd))

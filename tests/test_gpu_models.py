@@ -1,0 +1,244 @@
+"""GPU end-to-end tests through the reference-facing classes (NumPy in / NumPy out), mirroring the
+reference's own scripts (tests/test_mfgp_adapt_2d.py, tests/test_mfgp_adapt_4d.py, tests/MFDF_tests.py)
+against the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import gpy_oracle as go
+from oracle import mfgp_oracle as mo
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg(gpu):
+    import multifidelity_datafusion_gps_b200 as pkg
+    return pkg
+
+
+def _data(dim, seed=10, n_lf=100, n_hf=5, n_test=100):
+    # tests/utils.py:11,30-35
+    rs = np.random.RandomState(seed)
+    X_lf = rs.uniform(size=(n_lf, dim))
+    X_hf = rs.uniform(size=(n_hf, dim))
+    X_test = rs.uniform(size=(n_test, dim))
+    return X_lf, X_hf, X_test
+
+
+THETA_C = np.array([1.0, 0.8, 1.0, 0.5, 0.1, 0.3, 1e-3])
+THETA_R = np.array([1.2, 0.9, 1e-3])
+
+
+def test_config1_nargp_1d_callable_lf_fixed_theta(pkg):
+    # config 1: 1-D, f_low = sin 8 pi t, f_high = sin^2 8 pi t (src/data/exampleCurves1D.py:10-13)
+    hf_X = np.linspace(0, 1, 10)[:, None]
+    Xt = np.linspace(0, 1, 1000)[:, None]                       # src/abstractMFGP.py:288
+    m = pkg.NARGP(1, util.f_high_1d, util.f_low_1d)
+    m.fit(hf_X, theta=THETA_C)
+    o = mo.OracleMFGP(1, 0, 0, util.f_high_1d, f_low=util.f_low_1d)
+    o.fit(hf_X, theta=THETA_C)
+    mean, var = m.predict(Xt)
+    mu_ref, var_ref = o.predict(Xt)
+    assert mean.shape == (1000, 1) and var.shape == (1000, 1)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+    assert util.rel_err(var, var_ref, THETA_C[0] * THETA_C[2] + THETA_C[4]) < 1e-6
+    assert np.isclose(m.get_mse(Xt, util.f_high_1d(Xt)), o.get_mse(Xt, util.f_high_1d(Xt)), rtol=1e-6)
+
+
+def test_config1_nargp_1d_data_driven_lf(pkg):
+    rs = np.random.RandomState(42)
+    lf_X = rs.uniform(size=(50, 1))
+    lf_Y = util.f_low_1d(lf_X)
+    hf_X = np.linspace(0, 1, 10)[:, None]
+    Xt = np.linspace(0, 1, 400)[:, None]
+    lf_theta = np.array([1.0, 0.12, 1e-4])
+    m = pkg.NARGP(1, util.f_high_1d, None, lf_X=lf_X, lf_Y=lf_Y)
+    m.lf_model._set_params(lf_theta)          # fixed-theta parity: skip comparing optimiser paths
+    m.fit(hf_X, theta=THETA_C)
+    o = mo.OracleMFGP(1, 0, 0, util.f_high_1d, lf_X=lf_X, lf_Y=lf_Y, lf_theta=lf_theta)
+    o.fit(hf_X, theta=THETA_C)
+    assert util.rel_err(m.hf_model.X, o.hf_model.X) < 1e-9     # augmentation through the LF GP
+    mean, var = m.predict(Xt)
+    mu_ref, var_ref = o.predict(Xt)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+    assert util.rel_err(var, var_ref, 1.1) < 1e-6
+    # f_low attribute keeps the reference's contract: mean predictor of the LF GP
+    assert util.rel_err(m.f_low(Xt[:9]), o.f_low(Xt[:9])) < 1e-8
+
+
+@pytest.mark.parametrize("model", ["GPDF", "GPDFC"])
+def test_config2_gpdf_2d_delays_fixed_theta(pkg, model):
+    # tests/test_mfgp_adapt_2d.py:27: GPDF(dim=2, tau=0.001, num_derivatives=2) -> D = 7
+    _, X_hf, X_test = _data(2)
+    X_hf = np.vstack([X_hf, np.random.RandomState(3).uniform(size=(25, 2))])   # N_h 5 -> 30
+    composite = model == "GPDFC"
+    theta = THETA_C if composite else THETA_R
+    cls = getattr(pkg, model)
+    m = cls(2, 0.001, 2, util.hf_2d, util.lf_2d)
+    m.fit(X_hf, theta=theta)
+    assert m.hf_model.X.shape == (30, 7)
+    o = mo.OracleMFGP(2, 2, 0.001, util.hf_2d, f_low=util.lf_2d, use_composite_kernel=composite)
+    o.fit(X_hf, theta=theta)
+    assert np.array_equal(m.hf_model.X, o.hf_model.X)
+    mean, var = m.predict(X_test)
+    mu_ref, var_ref = o.predict(X_test)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+    assert util.rel_err(var, var_ref, 1.2) < 1e-6
+
+
+def test_add_noise_refactorises_at_1e_6(pkg):
+    _, X_hf, X_test = _data(2)
+    m = pkg.GPDF(2, 0.001, 2, util.hf_2d, util.lf_2d, add_noise=True)
+    m.fit(X_hf, theta=THETA_R)
+    o = mo.OracleMFGP(2, 2, 0.001, util.hf_2d, f_low=util.lf_2d, use_composite_kernel=False, add_noise=True)
+    o.fit(X_hf, theta=THETA_R)
+    mean, var = m.predict(X_test)
+    mu_ref, var_ref = o.predict(X_test)
+    assert m.hf_model.likelihood.variance == 1e-6
+    assert util.rel_err(mean, mu_ref) < 1e-7        # cond(K_y) ~ 1e6 at noise 1e-6
+    assert util.rel_err(var, var_ref, 1.2) < 1e-6
+
+
+def test_fit_reaches_oracle_likelihood(pkg):
+    # optimiser trajectories are not comparable (global NumPy RNG, SciPy version); the achieved LML is
+    np.random.seed(0)
+    _, X_hf, _ = _data(2, n_hf=12)
+    m = pkg.GPDF(2, 0.001, 2, util.hf_2d, util.lf_2d)
+    m.fit(X_hf)
+    o = mo.OracleMFGP(2, 2, 0.001, util.hf_2d, f_low=util.lf_2d, use_composite_kernel=False,
+                      rng=np.random.RandomState(0))
+    o.fit(X_hf)
+    ours = m.hf_model.log_likelihood()
+    theirs = o.hf_model.log_likelihood()
+    assert ours >= theirs - 1e-6 * abs(theirs) - 1e-3
+    # and the fitted theta evaluates to the same LML on the oracle
+    chk = go.inference(go.KIND_RBF, o.hf_model.X, o.hf_model.Y, 2, m.hf_model.param_array, want_grad=False)
+    assert abs(chk["lml"] - ours) <= 1e-6 * abs(ours) + 1e-9
+
+
+def test_adaptation_with_candidate_set_improves_mse_and_matches_oracle_argmax(pkg):
+    # tests/MFDF_tests.py:10-26 asserts mse_after < mse_before; the arg-max index must be bit-exact
+    np.random.seed(1)
+    _, X_hf, X_test = _data(2, n_hf=6)
+    cands = np.random.default_rng(0).uniform(size=(100000, 2))
+    mx = pkg.CandidateSetMaximizer(candidates=cands)
+    m = pkg.GPDF(2, 0.001, 2, util.hf_2d, util.lf_2d, adapt_maximizer=mx)
+    m.fit(X_hf)
+    Y_test = util.hf_2d(X_test)
+    mse_before = m.get_mse(X_test, Y_test)
+    # index parity at the fitted theta
+    o = mo.OracleMFGP(2, 2, 0.001, util.hf_2d, f_low=util.lf_2d, use_composite_kernel=False)
+    o.fit(X_hf, theta=m.hf_model.param_array)
+    i_ref, x_ref, fopt_ref, gap = mo.candidate_argmax(o.predict, cands)
+    idx, val = m.acquisition_argmax(cands)
+    if gap > 1e-9:
+        assert idx == i_ref
+    assert abs(-val - fopt_ref) <= 1e-6 * abs(fopt_ref)
+    m.adapt(5, eps=0.0)
+    assert m.hf_X.shape == (11, 2) and m.adapt_steps == 5 and len(m.acquired_points) == 5
+    assert m.get_mse(X_test, Y_test) < mse_before
+
+
+def test_config3_nargp_4d_candidates(pkg):
+    # tests/test_mfgp_adapt_4d.py: NARGP in 4-D (D = 5), 5 HF points; 1M candidates are covered by
+    # bench/scale runs, here 200k for the oracle's sake
+    _, X_hf, _ = _data(4)
+    cands = np.random.default_rng(0).uniform(size=(200000, 4))
+    m = pkg.NARGP(4, util.hf_4d, util.lf_4d)
+    m.fit(X_hf, theta=np.array([1.0, 0.3, 1.0, 0.3, 0.1, 0.3, 1e-3]))
+    o = mo.OracleMFGP(4, 0, 0, util.hf_4d, f_low=util.lf_4d)
+    o.fit(X_hf, theta=np.array([1.0, 0.3, 1.0, 0.3, 0.1, 0.3, 1e-3]))
+    i_ref, _, fopt_ref, gap = mo.candidate_argmax(o.predict, cands)
+    idx, val = m.acquisition_argmax(cands)
+    assert gap <= 1e-9 or idx == i_ref
+    assert abs(-val - fopt_ref) <= 1e-6 * abs(fopt_ref)
+
+
+def _mc_models(pkg, n_l=100, n_h=30, d=4, seed=4):
+    rs = np.random.RandomState(seed)
+    lf_X = rs.uniform(size=(n_l, d))
+    hf_X = rs.uniform(size=(n_h, d))
+    lf_theta = np.array([1.5, 0.6, 1e-3])
+    th = np.array([1.0, 0.5, 1.0, 0.6, 0.1, 0.5, 1e-3])
+    m = pkg.NARGP(d, util.hf_4d, None, lf_X=lf_X, lf_Y=util.lf_4d(lf_X))
+    m.lf_model._set_params(lf_theta)
+    m.fit(hf_X, theta=th)
+    o = mo.OracleMFGP(d, 0, 0, util.hf_4d, lf_X=lf_X, lf_Y=util.lf_4d(lf_X), lf_theta=lf_theta)
+    o.fit(hf_X, theta=th)
+    return m, o
+
+
+def test_mc_propagation_matches_oracle_with_supplied_normals(pkg):
+    m, o = _mc_models(pkg)
+    M, S = 500, 100
+    Xt = np.random.default_rng(5).uniform(size=(M, 4))
+    eps = np.random.default_rng(2).standard_normal((M, S, 1))
+    mean, var = m.predict_mc(Xt, n_samples=S, eps=eps)
+    mu_ref, var_ref = o.predict_mc(Xt, eps)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+    assert util.rel_err(var, var_ref, 1.1) < 1e-6
+
+
+def test_mc_one_sample_zero_eps_reproduces_predict(pkg):
+    # S = 1, eps = 0 must reproduce the reference predict()
+    m, o = _mc_models(pkg)
+    Xt = np.random.default_rng(6).uniform(size=(300, 4))
+    mean, var = m.predict_mc(Xt, n_samples=1, eps=np.zeros((300, 1)))
+    mu, v = m.predict(Xt)
+    assert util.rel_err(mean, mu) < 1e-12 and util.rel_err(var, v, 1.1) < 1e-10
+    mu_ref, var_ref = o.predict(Xt)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+
+
+def test_mc_in_kernel_philox_matches_oracle_and_pce_mean(pkg):
+    from multifidelity_datafusion_gps_b200 import ops
+    m, o = _mc_models(pkg)
+    nodes, w = mo.gauss_legendre_grid(3, 4)                      # 4^4 = 256 quadrature nodes
+    M, S, seed = nodes.shape[0], 32, 2
+    mean, var = m.predict_mc(nodes, n_samples=S, seed=seed, weights=w)
+    eps = ops.fill_normal(seed, 0, M * S, "cuda:0").cpu().numpy().reshape(M, S, 1)
+    mu_ref, var_ref = o.predict_mc(nodes, eps)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+    assert util.rel_err(var, var_ref, 1.1) < 1e-6
+    assert np.isclose(m.last_pce_mean, float(np.sum(w * mu_ref[:, 0])), rtol=1e-9)
+    # sharding invariance: points [128, 256) evaluated alone with m0 = 128 give the same bits
+    import torch
+    dX = torch.from_numpy(nodes[128:]).to("cuda:0")
+    mean2, var2, _ = m.predict_mc_device(dX, S, None, seed, 128)
+    assert np.array_equal(mean2.cpu().numpy(), mean[128:, 0]) and np.array_equal(var2.cpu().numpy(), var[128:, 0])
+
+
+def test_assertions_mirror_reference(pkg):
+    m = pkg.NARGP(2, util.hf_2d, util.lf_2d)
+    with pytest.raises(AssertionError):
+        m.fit(np.zeros((5, 3)))                                 # src/MFDataFusion.py:84
+    with pytest.raises(AssertionError):
+        m.fit(np.zeros(5))                                      # :83
+    m.fit(np.random.RandomState(0).uniform(size=(5, 2)), theta=THETA_C)
+    with pytest.raises(AssertionError):
+        m.predict(np.zeros((4, 3)))                             # :152
+    with pytest.raises(AssertionError):
+        m.get_mse(np.zeros((4, 2)), np.zeros((3, 1)))           # :169
+    with pytest.raises(AssertionError):
+        pkg.NARGP(2, util.hf_2d, None)                          # src/abstractMFGP.py:93-95
+    with pytest.raises(AssertionError):
+        m.adapt(1, plot_mode="x")                               # src/MFDataFusion.py:138
+
+
+def test_jitter_retry_on_duplicate_rows(pkg):
+    # duplicated HF points with (almost) no noise -> first Cholesky fails, GPy's jitter schedule kicks in
+    from multifidelity_datafusion_gps_b200 import gp
+    X = np.repeat(np.random.RandomState(0).uniform(size=(6, 2)), 2, axis=0)
+    Y = util.hf_2d(X)
+    model = gp.GPRegression(X, Y)
+    model._set_params(np.array([1.0, 1.0, 0.0]))
+    model._dA.fill_(0)
+    # K + 1e-8 I is numerically singular here or not; force the issue with a negative-definite shift
+    try:
+        model._ensure_posterior()
+    except gp.NotPositiveDefinite:
+        pytest.fail("jitter schedule exhausted")
+    assert model.last_jitter >= 0.0
+    mu, _ = model.predict(X)
+    assert util.rel_err(mu, Y) < 1e-3
