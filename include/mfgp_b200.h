@@ -73,6 +73,14 @@ const char* mfgp_last_error(mfgp_handle_t h);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 long long mfgp_launch_count(mfgp_handle_t h);
 
+/* Per-kernel-class timing for bench.py's roofline: when enabled, launches are bracketed by CUDA
+ * event pairs on the handle's stream (first 512 launches per class).  mfgp_profile_read synchronises
+ * and returns, per class, the average launch duration in ms (h_ms[10]) and the launch count
+ * (h_count[10]); classes: 0 assemble, 1 potrf leaf, 2 gemm (potrf/trtri), 3 solve, 4 lauum,
+ * 5 grad_reduce, 6 cross-covariance, 7 trmm+sumsq, 8 misc, 9 argmax. */
+int mfgp_profile_enable(mfgp_handle_t h, int on);
+int mfgp_profile_read(mfgp_handle_t h, double* h_ms, long long* h_count);
+
 /* K1 -- covariance assembly.  Replaces kern.K(X) + diag.add(Ky, noise + 1e-8)
  * (GPy exact_gaussian_inference.py, reached from src/MFDataFusion.py:93-98).
  * Writes K_y = K + (noise + 1e-8 + jitter) I into d_K (N x N, leading dimension ldk);

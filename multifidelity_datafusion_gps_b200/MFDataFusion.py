@@ -186,8 +186,10 @@ class MultifidelityDataFusion(AbstractMFGP):
             ws.data_ptr(), ws.numel() * 8))
         return mean, var, (wsum.value if wsum is not None else None)
 
-    def predict_mc(self, X_test, n_samples=100, eps=None, seed=0, weights=None, include_lf_noise=True):
+    def predict_mc(self, X_test, n_samples=100, eps=None, seed=0, weights=None, include_lf_noise=True,
+                   m0=0):
         """NumPy front end of predict_mc_device.  eps: optional (M, S) or (M, S, 1) standard normals.
+        m0: global index of the first test point (keys the in-kernel generator when eps is None).
         Returns (mean (M,1), var (M,1)); with `weights` also sets ``self.last_pce_mean``."""
         assert X_test.ndim == 2 and X_test.shape[1] == self.input_dim
         d_eps = None
@@ -196,7 +198,7 @@ class MultifidelityDataFusion(AbstractMFGP):
             d_eps = gp.to_device(eps, self.device)
         d_w = gp.to_device(np.asarray(weights).ravel(), self.device) if weights is not None else None
         mean, var, wsum = self.predict_mc_device(gp.to_device(X_test, self.device), n_samples, d_eps,
-                                                 seed, 0, d_w, include_lf_noise)
+                                                 seed, m0, d_w, include_lf_noise)
         self.last_pce_mean = wsum
         return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]
 

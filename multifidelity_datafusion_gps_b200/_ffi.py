@@ -18,7 +18,7 @@ TILE = 128
 
 EXPORTS = [
     "mfgp_version", "mfgp_padded_n", "mfgp_create", "mfgp_destroy", "mfgp_set_stream",
-    "mfgp_last_error", "mfgp_launch_count", "mfgp_assemble", "mfgp_factorize", "mfgp_lml_grad",
+    "mfgp_last_error", "mfgp_launch_count", "mfgp_profile_enable", "mfgp_profile_read", "mfgp_assemble", "mfgp_factorize", "mfgp_lml_grad",
     "mfgp_lml_grad_timed", "mfgp_potrf", "mfgp_trtri", "mfgp_lauum", "mfgp_predict_ws_bytes",
     "mfgp_predict", "mfgp_augment", "mfgp_predict_mc", "mfgp_fill_normal", "mfgp_argmax",
 ]
@@ -68,6 +68,8 @@ def load_library():
     lib.mfgp_last_error.restype = ctypes.c_char_p
     lib.mfgp_launch_count.argtypes = [vp]
     lib.mfgp_launch_count.restype = c_ll
+    lib.mfgp_profile_enable.argtypes = [vp, c_int]
+    lib.mfgp_profile_read.argtypes = [vp, vp, vp]
     lib.mfgp_assemble.argtypes = [vp, c_int, vp, c_int, c_int, c_int, vp, c_int, c_dbl, vp, c_ll, c_int]
     lib.mfgp_factorize.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, c_dbl, vp, vp, vp, vp]
     lib.mfgp_lml_grad.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, c_dbl, vp, vp, vp, vp, vp]
@@ -129,6 +131,20 @@ class Handle:
 
     def set_stream(self, stream_ptr):
         self.check(self.lib.mfgp_set_stream(self.h, ctypes.c_void_p(stream_ptr)))
+
+    PROFILE_CLASSES = ["assemble", "potrf_leaf", "gemm", "solve", "lauum", "grad_reduce", "cross_gen",
+                       "trmm_sumsq", "misc", "argmax"]
+
+    def profile_enable(self, on=True):
+        self.check(self.lib.mfgp_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{class: (average launch ms, launches)} since profile_enable."""
+        ms = (ctypes.c_double * 16)()
+        cnt = (ctypes.c_longlong * 16)()
+        self.check(self.lib.mfgp_profile_read(self.h, ctypes.cast(ms, ctypes.c_void_p),
+                                              ctypes.cast(cnt, ctypes.c_void_p)))
+        return {n: (ms[i], int(cnt[i])) for i, n in enumerate(self.PROFILE_CLASSES)}
 
     @property
     def launches(self):

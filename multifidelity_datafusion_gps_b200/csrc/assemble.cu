@@ -237,10 +237,12 @@ int assemble_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, doub
   const int lower = uplo == MFGP_UPLO_LOWER;
   const int grid = lower ? tiles * (tiles + 1) / 2 : tiles * tiles;
   const bool vec = (nrows % AT == 0) && (ldk % 2 == 0) && ((uintptr_t)K % 16 == 0);
+  prof_begin(h, PC_ASSEMBLE);
   if (vec)
     assemble_kernel<true><<<grid, 256, 0, h->stream>>>(kp, X, N, diag_add, K, ldk, lower, tiles, nrows);
   else
     assemble_kernel<false><<<grid, 256, 0, h->stream>>>(kp, X, N, diag_add, K, ldk, lower, tiles, nrows);
+  prof_end(h, PC_ASSEMBLE);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -250,7 +252,9 @@ int grad_reduce_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, c
   const int tiles = (N + AT - 1) / AT;
   const int nlin = tiles * (tiles + 1) / 2;
   const int grid = nlin < GR_BLOCKS ? nlin : GR_BLOCKS;
+  prof_begin(h, PC_GRAD);
   grad_reduce_kernel<<<grid, 256, 0, h->stream>>>(kp, X, N, Kinv, ld, alpha, nlin, h->d_partials);
+  prof_end(h, PC_GRAD);
   LAUNCH_CHECK(h);
   reduce_partials_kernel<<<1, 192, 0, h->stream>>>(h->d_partials, grid, d_out8);
   LAUNCH_CHECK(h);

@@ -34,7 +34,26 @@ struct mfgp_ctx {
   double* h_pinned;       // 64 doubles pinned
   int* h_info;            // 4 ints pinned
   cudaEvent_t ev[8];
+  // optional per-kernel-class timing (mfgp_profile_enable): event pairs around launches
+  int prof_on;
+  cudaEvent_t* prof_ev;                 // [MFGP_PROF_CLASSES][MFGP_PROF_POOL][2]
+  long long prof_count[16];             // launches seen per class since enable/reset
 };
+
+#define MFGP_PROF_CLASSES 10
+#define MFGP_PROF_POOL 512
+enum { PC_ASSEMBLE = 0, PC_LEAF, PC_GEMM, PC_SOLVE, PC_LAUUM, PC_GRAD, PC_CROSSGEN, PC_TRMM_SUMSQ, PC_MISC, PC_ARGMAX };
+
+static inline void prof_begin(mfgp_ctx* h, int cls) {
+  if (!h->prof_on) return;
+  long long c = h->prof_count[cls];
+  if (c < MFGP_PROF_POOL) cudaEventRecord(h->prof_ev[(cls * MFGP_PROF_POOL + c) * 2], h->stream);
+}
+static inline void prof_end(mfgp_ctx* h, int cls) {
+  if (!h->prof_on) return;
+  long long c = h->prof_count[cls]++;
+  if (c < MFGP_PROF_POOL) cudaEventRecord(h->prof_ev[(cls * MFGP_PROF_POOL + c) * 2 + 1], h->stream);
+}
 
 #define MFGP_PARTIALS (1 << 16)
 

@@ -2,27 +2,43 @@
 //
 // tcgen05/UMMA has no FP64 kind, and every mma.sync f64 shape (m8n8k4, m16n8k4/8/16) lowers to
 // DMMA.8x8x4 on sm_100a (checked with cuobjdump), so the FP64 tensor path on B200 is the warp-level
-// DMMA.8x8x4 fed from shared memory.  This core is a 128x128x16 CTA tile, 8 warps of 64x32,
-// 4-stage cp.async (LDGSTS) pipeline, conflict-free padded shared-memory layouts.
+// DMMA.8x8x4 fed from shared memory.  The core is a BMxBNx16 CTA tile with a 4-stage cp.async
+// (LDGSTS) pipeline and conflict-free padded shared-memory layouts; two instantiations are used:
+//   Big   128x128, 8 warps of 64x32  -- throughput shape (1 CTA / SM, 160 KB smem)
+//   Small  64x64,  4 warps of 32x32  -- latency shape for the narrow GEMMs on the critical path of the
+//                                       recursive factorisation (4x the CTAs, 2 CTAs / SM)
 //
 //   C[m][n] (+)= alpha * sum_k A(m,k) * B(n,k)
 //
 // Operand layouts (template flags):
 //   A_KC = true : A(m,k) = A[m*lda + k]   (k contiguous)     false: A(m,k) = A[k*lda + m]
 //   B_KC = true : B(n,k) = B[n*ldb + k]   (k contiguous)     false: B(n,k) = B[k*ldb + n]
-// All extents are multiples of the tile (the factor buffers are padded to 128, see common.cuh), all
-// leading dimensions are even and all base pointers 16-byte aligned, so there is no edge handling.
+// All extents are multiples of 128 (the factor buffers are padded, see common.cuh), all leading
+// dimensions are even and all base pointers 16-byte aligned, so there is no edge handling.
 #pragma once
 #include "common.cuh"
 
 namespace dg {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
-constexpr int KC_STRIDE = BK + 4;    // [rows][BK] tile, row stride 20 doubles (== 4 mod 16 -> no LDS conflicts)
-constexpr int MC_STRIDE = BM + 4;    // [BK][rows] tile, row stride 132 doubles (== 4 mod 16)
-constexpr int OP_STAGE = BM * KC_STRIDE;              // 2560 doubles >= BK*MC_STRIDE (2112)
-constexpr int STAGE_DOUBLES = 2 * OP_STAGE;
-constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163840
+constexpr int BK = 16, STAGES = 4;
+constexpr int KC_STRIDE = BK + 4;   // [rows][BK] tile: row stride 20 doubles (== 4 mod 16 -> no LDS conflicts)
+
+template <int BM_, int BN_, int WGM_, int WGN_>
+struct TileCfg {
+  static constexpr int BM = BM_, BN = BN_, WGM = WGM_, WGN = WGN_;
+  static constexpr int THREADS = 32 * WGM * WGN;
+  static constexpr int WTM = BM / WGM, WTN = BN / WGN;   // warp tile
+  static constexpr int MT = WTM / 8, NT = WTN / 8;       // 8x8 DMMA tiles per warp
+  static constexpr int A_MC_STRIDE = BM + 4;             // [BK][rows] tile: stride == 4 mod 16
+  static constexpr int B_MC_STRIDE = BN + 4;
+  static constexpr int A_STAGE = (BM * KC_STRIDE > BK * A_MC_STRIDE) ? BM * KC_STRIDE : BK * A_MC_STRIDE;
+  static constexpr int B_STAGE = (BN * KC_STRIDE > BK * B_MC_STRIDE) ? BN * KC_STRIDE : BK * B_MC_STRIDE;
+  static constexpr int STAGE_DOUBLES = A_STAGE + B_STAGE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
+};
+using Big = TileCfg<128, 128, 2, 4>;     // 163840 B smem
+using Small = TileCfg<64, 64, 2, 2>;     //  81920 B smem
+using Row32 = TileCfg<32, 128, 1, 4>;    // 102400 B smem: owns all 128 columns of its 32 rows (in-place TRSM leaf)
 
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -40,43 +56,46 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-template <bool KC>
+// one BK-deep slab of an operand: ROWS x BK doubles = ROWS*8 16-byte chunks
+template <bool KC, int ROWS, int THREADS>
 __device__ __forceinline__ void load_operand(double* sdst, const double* g, long ld, int r0, int k0,
                                              int tid) {
+  constexpr int PER_THREAD = ROWS * 8 / THREADS;
+  constexpr int MC_STRIDE = ROWS + 4;
   if (KC) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < PER_THREAD; i++) {
       int c = tid + i * THREADS;
       int r = c >> 3, kc = c & 7;
       cp_async16(sdst + r * KC_STRIDE + kc * 2, g + (long)(r0 + r) * ld + k0 + kc * 2);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < PER_THREAD; i++) {
       int c = tid + i * THREADS;
-      int kr = c >> 6, mc = c & 63;
+      int kr = c / (ROWS / 2), mc = c % (ROWS / 2);
       cp_async16(sdst + kr * MC_STRIDE + mc * 2, g + (long)(k0 + kr) * ld + r0 + mc * 2);
     }
   }
 }
 
 // acc[i][j][e]: m-tile i (8 rows each), n-tile j (8 cols each); lane holds row g, cols 2t+e.
-template <bool A_KC, bool B_KC>
-__device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* A, long lda,
+template <class T, bool A_KC, bool B_KC>
+__device__ __forceinline__ void mainloop(double (&acc)[T::MT][T::NT][2], const double* A, long lda,
                                          const double* B, long ldb, int row0, int col0, int k_begin,
                                          int k_end, double* smem) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int wm0 = (warp / T::WGN) * T::WTM, wn0 = (warp % T::WGN) * T::WTN;
   const int nk = (k_end - k_begin) / BK;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; s++) {
     if (s < nk) {
-      double* sa = smem + s * STAGE_DOUBLES;
-      load_operand<A_KC>(sa, A, lda, row0, k_begin + s * BK, tid);
-      load_operand<B_KC>(sa + OP_STAGE, B, ldb, col0, k_begin + s * BK, tid);
+      double* sa = smem + s * T::STAGE_DOUBLES;
+      load_operand<A_KC, T::BM, T::THREADS>(sa, A, lda, row0, k_begin + s * BK, tid);
+      load_operand<B_KC, T::BN, T::THREADS>(sa + T::A_STAGE, B, ldb, col0, k_begin + s * BK, tid);
     }
     cp_async_commit();
   }
@@ -87,29 +106,29 @@ __device__ __forceinline__ void mainloop(double (&acc)[8][4][2], const double* A
     {
       int nxt = kt + STAGES - 1;
       if (nxt < nk) {
-        double* sa = smem + (nxt % STAGES) * STAGE_DOUBLES;
-        load_operand<A_KC>(sa, A, lda, row0, k_begin + nxt * BK, tid);
-        load_operand<B_KC>(sa + OP_STAGE, B, ldb, col0, k_begin + nxt * BK, tid);
+        double* sa = smem + (nxt % STAGES) * T::STAGE_DOUBLES;
+        load_operand<A_KC, T::BM, T::THREADS>(sa, A, lda, row0, k_begin + nxt * BK, tid);
+        load_operand<B_KC, T::BN, T::THREADS>(sa + T::A_STAGE, B, ldb, col0, k_begin + nxt * BK, tid);
       }
       cp_async_commit();
     }
-    const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
-    const double* sb = sa + OP_STAGE;
+    const double* sa = smem + (kt % STAGES) * T::STAGE_DOUBLES;
+    const double* sb = sa + T::A_STAGE;
 #pragma unroll
     for (int kk = 0; kk < BK / 4; kk++) {
-      double a[8], b[4];
+      double a[T::MT], b[T::NT];
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+      for (int i = 0; i < T::MT; i++)
         a[i] = A_KC ? sa[(wm0 + 8 * i + g) * KC_STRIDE + kk * 4 + t]
-                    : sa[(kk * 4 + t) * MC_STRIDE + wm0 + 8 * i + g];
+                    : sa[(kk * 4 + t) * T::A_MC_STRIDE + wm0 + 8 * i + g];
 #pragma unroll
-      for (int j = 0; j < 4; j++)
+      for (int j = 0; j < T::NT; j++)
         b[j] = B_KC ? sb[(wn0 + 8 * j + g) * KC_STRIDE + kk * 4 + t]
-                    : sb[(kk * 4 + t) * MC_STRIDE + wn0 + 8 * j + g];
+                    : sb[(kk * 4 + t) * T::B_MC_STRIDE + wn0 + 8 * j + g];
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+      for (int i = 0; i < T::MT; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int j = 0; j < T::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
   cp_async_wait<0>();
@@ -123,14 +142,14 @@ struct GemmParams {
   long ldb;
   double* C;
   long ldc;
-  int tiles_m, tiles_n, K;
+  int M, N, K;                         // extents (multiples of 128)
   double alpha, beta;
-  int lower_only;                      // enumerate only tiles with ti >= tj (tiles_m == tiles_n)
+  int lower_only;                      // enumerate only tiles with ti >= tj (M == N)
   int kb_row, kb_col, ke_row;          // triangular operands: k >= row0 / k >= col0 / k < row0+BM
 };
 
-template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmParams p) {
+template <class T, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(T::THREADS) gemm_kernel(GemmParams p) {
   extern __shared__ __align__(16) double smem[];
   int ti, tj;
   if (p.lower_only) {
@@ -140,31 +159,33 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmParams p) {
     while ((long)ti * (ti + 1) / 2 > tt) ti--;
     tj = tt - ti * (ti + 1) / 2;
   } else {
-    ti = blockIdx.x / p.tiles_n;
-    tj = blockIdx.x % p.tiles_n;
+    const int tiles_n = p.N / T::BN;
+    ti = blockIdx.x / tiles_n;
+    tj = blockIdx.x % tiles_n;
   }
-  const int row0 = ti * BM, col0 = tj * BN;
+  const int row0 = ti * T::BM, col0 = tj * T::BN;
   int kb = 0, ke = p.K;
+  // k-ranges are rounded outwards to BK; the operands hold explicit zeros there
   if (p.kb_row) kb = max(kb, row0);
   if (p.kb_col) kb = max(kb, col0);
-  if (p.ke_row) ke = min(ke, row0 + BM);
+  if (p.ke_row) ke = min(ke, row0 + T::BM);
 
-  double acc[8][4][2];
+  double acc[T::MT][T::NT][2];
 #pragma unroll
-  for (int i = 0; i < 8; i++)
+  for (int i = 0; i < T::MT; i++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < T::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  if (ke > kb) mainloop<A_KC, B_KC>(acc, p.A, p.lda, p.B, p.ldb, row0, col0, kb, ke, smem);
+  if (ke > kb) mainloop<T, A_KC, B_KC>(acc, p.A, p.lda, p.B, p.ldb, row0, col0, kb, ke, smem);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int wm0 = (warp / T::WGN) * T::WTM, wn0 = (warp % T::WGN) * T::WTN;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
+  for (int i = 0; i < T::MT; i++) {
     const long r = row0 + wm0 + 8 * i + g;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < T::NT; j++) {
       double2* ptr = reinterpret_cast<double2*>(p.C + r * p.ldc + col0 + wn0 + 8 * j + 2 * t);
       double2 v;
       v.x = p.alpha * acc[i][j][0];
@@ -182,36 +203,37 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(GemmParams p) {
 // tmp = W * Ks^T with fused column sum of squares; one CTA owns a 128-column tile of Ks and walks
 // all row tiles of the lower-triangular W (k < row0+128), so the reduction order is fixed.
 //   out_ss[c] = sum_i ( sum_{k<=i} W[i][k] * Ks[c][k] )^2
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(Big::THREADS, 1)
     trmm_sumsq_kernel(const double* W, int npad, const double* Ks, double* out_ss) {
+  using T = Big;
   extern __shared__ __align__(16) double smem[];
-  __shared__ double red[2][BN];
-  const int col0 = blockIdx.x * BN;
+  __shared__ double red[2][T::BN];
+  const int col0 = blockIdx.x * T::BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wn0 = (warp & 3) * 32;
-  double ss[4][2];
+  const int wn0 = (warp % T::WGN) * T::WTN;
+  double ss[T::NT][2];
 #pragma unroll
-  for (int j = 0; j < 4; j++) ss[j][0] = ss[j][1] = 0.0;
+  for (int j = 0; j < T::NT; j++) ss[j][0] = ss[j][1] = 0.0;
 
-  for (int ti = 0; ti < npad / BM; ti++) {
-    double acc[8][4][2];
+  for (int ti = 0; ti < npad / T::BM; ti++) {
+    double acc[T::MT][T::NT][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < T::MT; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    mainloop<true, true>(acc, W, npad, Ks, npad, ti * BM, col0, 0, ti * BM + BM, smem);
+      for (int j = 0; j < T::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    mainloop<T, true, true>(acc, W, npad, Ks, npad, ti * T::BM, col0, 0, ti * T::BM + T::BM, smem);
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < T::MT; i++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < T::NT; j++) {
         ss[j][0] = fma(acc[i][j][0], acc[i][j][0], ss[j][0]);
         ss[j][1] = fma(acc[i][j][1], acc[i][j][1], ss[j][1]);
       }
   }
   // reduce over the 8 row groups g (lanes with equal t), then over the two warp rows
 #pragma unroll
-  for (int j = 0; j < 4; j++)
+  for (int j = 0; j < T::NT; j++)
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       double v = ss[j][e];
@@ -222,13 +244,13 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
   if (g == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      red[warp >> 2][wn0 + 8 * j + 2 * t] = ss[j][0];
-      red[warp >> 2][wn0 + 8 * j + 2 * t + 1] = ss[j][1];
+    for (int j = 0; j < T::NT; j++) {
+      red[warp / T::WGN][wn0 + 8 * j + 2 * t] = ss[j][0];
+      red[warp / T::WGN][wn0 + 8 * j + 2 * t + 1] = ss[j][1];
     }
   }
   __syncthreads();
-  if (threadIdx.x < BN) out_ss[col0 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x];
+  if (threadIdx.x < T::BN) out_ss[col0 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x];
 }
 
 }  // namespace dg

@@ -16,69 +16,135 @@ namespace {
 constexpr int LEAF = 128;
 constexpr int LEAF_LD = LEAF + 1;
 
-// One CTA factorises a 128x128 diagonal block in shared memory and inverts the factor.
-// L is kept in the lower triangle of S, the columns of W = L^-1 are built in the upper triangle.
-__global__ void __launch_bounds__(256, 1)
-    leaf_potrf_inv_kernel(double* A, long lda, double* W, long ldw, int* info, int j0) {
-  extern __shared__ double S[];   // LEAF x LEAF_LD
-  __shared__ double dinv[LEAF], dsq[LEAF];
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
-    int i = idx >> 7, j = idx & 127;
-    S[i * LEAF_LD + j] = A[(long)i * lda + j];
-  }
-  __syncthreads();
-  for (int k = 0; k < LEAF; k++) {
-    __syncthreads();   // trailing update of step k-1 is complete
-    double p = S[k * LEAF_LD + k];
+// One CTA factorises a 128x128 diagonal block and inverts the factor, with the whole block
+// REGISTER-resident: thread (ty,tx) of the 16x16 thread grid owns the 2-D cyclic 8x8 element set
+// (i = ty+16a, j = tx+16b).  Positions with j <= i hold A -> L; positions with j > i hold the
+// accumulators of W = L^-1 transposed (position (r,c), r < c, works on W[c][r]).  Per elimination
+// step only column k of that packed matrix goes through shared memory (double-buffered, one
+// __syncthreads per step); the rank-1 updates are pure register FMAs.
+constexpr int LT = 16;   // thread grid edge; 8 = LEAF / LT elements per thread and dimension
+
+template <int KB>
+__device__ __forceinline__ void leaf_chol_block(double (&t)[8][8], double (*col)[LEAF], double* dinv,
+                                                int tx, int ty, int* info, int j0) {
+  for (int ko = 0; ko < LT; ko++) {
+    const int k = KB * LT + ko;
+    double* buf = col[k & 1];
+    if (tx == ko) {   // owners of column k publish it (unscaled), rows >= k only matter
+#pragma unroll
+      for (int a = KB; a < 8; a++) buf[ty + LT * a] = t[a][KB];
+    }
+    __syncthreads();
+    double p = buf[k];
     if (!(p > 0.0)) {   // also catches NaN
-      if (tid == 0 && info[0] == 0) info[0] = j0 + k + 1;
+      if (tx == 0 && ty == 0 && info[0] == 0) info[0] = j0 + k + 1;
       p = 1.0;
     }
-    const double lkk = sqrt(p);
-    const double rinv = 1.0 / lkk;
-    if (tid == 0) {
-      dsq[k] = lkk;     // S[k][k] itself is left untouched: other threads may still be reading it
-      dinv[k] = rinv;
+    const double rinv = rsqrt(p);
+    if (tx == ko) {   // owners keep the scaled column = column k of L
+#pragma unroll
+      for (int a = KB; a < 8; a++) {
+        const int i = ty + LT * a;
+        if (i > k) t[a][KB] *= rinv;
+        else if (i == k) { t[a][KB] = p * rinv; dinv[k] = rinv; }
+      }
     }
-    for (int i = k + 1 + tid; i < LEAF; i += 256) S[i * LEAF_LD + k] *= rinv;
+    double li[8], lj[8];
+#pragma unroll
+    for (int a = KB; a < 8; a++) li[a] = buf[ty + LT * a] * rinv;
+#pragma unroll
+    for (int b = KB; b < 8; b++) lj[b] = buf[tx + LT * b] * rinv;
+#pragma unroll
+    for (int a = KB; a < 8; a++) {
+      if (a == KB && ty <= ko) continue;          // row i <= k
+#pragma unroll
+      for (int b = KB; b <= a; b++) {
+        if (b == KB && tx <= ko) continue;        // column j <= k
+        if (a == b && tx > ty) continue;          // strictly upper position
+        t[a][b] = fma(-li[a], lj[b], t[a][b]);
+      }
+    }
+  }
+}
+
+template <int KB>
+__device__ __forceinline__ void leaf_inv_block(double (&t)[8][8], double (*col)[LEAF], const double* dinv,
+                                               int tx, int ty) {
+  for (int ko = 0; ko < LT; ko++) {
+    const int k = KB * LT + ko;
+    double* buf = col[k & 1];
+    if (tx == ko) {   // column k of the packed matrix: r < k -> acc of W[k][r]; r > k -> L[r][k]
+#pragma unroll
+      for (int a = 0; a < 8; a++) buf[ty + LT * a] = t[a][KB];
+    }
     __syncthreads();
-    // trailing update of the lower triangle: S[i][j] -= S[i][k] * S[j][k], k < j <= i
-    const int n = LEAF - k - 1;
-    for (int ii = tid >> 4; ii < n; ii += 16) {
-      const int i = k + 1 + ii;
-      const double lik = S[i * LEAF_LD + k];
-      for (int jj = tid & 15; jj <= ii; jj += 16) {
-        const int j = k + 1 + jj;
-        S[i * LEAF_LD + j] -= lik * S[j * LEAF_LD + k];
+    const double dk = dinv[k];
+    double wr[8], lc[8];
+#pragma unroll
+    for (int a = 0; a <= KB; a++) {               // W[k][r] for this thread's rows r <= k
+      const int r = ty + LT * a;
+      wr[a] = (r == k) ? dk : -dk * buf[r];
+    }
+#pragma unroll
+    for (int b = KB; b < 8; b++) lc[b] = buf[tx + LT * b];   // L[c][k] for this thread's columns c > k
+#pragma unroll
+    for (int a = 0; a <= KB; a++) {
+      if (a == KB && ty > ko) continue;           // row r > k
+#pragma unroll
+      for (int b = KB; b < 8; b++) {
+        if (b == KB && tx <= ko) continue;        // column c <= k
+        t[a][b] = fma(lc[b], wr[a], t[a][b]);     // acc(W[c][r]) += L[c][k] * W[k][r]
       }
     }
   }
-  __syncthreads();
-  // inverse: thread c builds column c of W by forward substitution, stored at S[c][i], i > c
-  if (tid < LEAF) {
-    const int c = tid;
-    const double wcc = dinv[c];
-    for (int i = c + 1; i < LEAF; i++) {
-      double s0 = S[i * LEAF_LD + c] * wcc, s1 = 0.0;
-      int k = c + 1;
-      for (; k + 1 < i; k += 2) {
-        s0 = fma(S[i * LEAF_LD + k], S[c * LEAF_LD + k], s0);
-        s1 = fma(S[i * LEAF_LD + k + 1], S[c * LEAF_LD + k + 1], s1);
-      }
-      if (k < i) s0 = fma(S[i * LEAF_LD + k], S[c * LEAF_LD + k], s0);
-      S[c * LEAF_LD + i] = -(s0 + s1) * dinv[i];
+}
+
+__global__ void __launch_bounds__(256, 1)
+    leaf_potrf_inv_kernel(double* A, long lda, double* W, long ldw, int* info, int j0) {
+  extern __shared__ double S[];   // LEAF x LEAF_LD staging for the coalesced write-out
+  __shared__ double col[2][LEAF];
+  __shared__ double dinv[LEAF];
+  const int tid = threadIdx.x;
+  const int tx = tid & (LT - 1), ty = tid >> 4;
+  double t[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int i = ty + LT * a, j = tx + LT * b;
+      t[a][b] = (j <= i) ? A[(long)i * lda + j] : 0.0;
     }
-  }
+  leaf_chol_block<0>(t, col, dinv, tx, ty, info, j0);
+  leaf_chol_block<1>(t, col, dinv, tx, ty, info, j0);
+  leaf_chol_block<2>(t, col, dinv, tx, ty, info, j0);
+  leaf_chol_block<3>(t, col, dinv, tx, ty, info, j0);
+  leaf_chol_block<4>(t, col, dinv, tx, ty, info, j0);
+  leaf_chol_block<5>(t, col, dinv, tx, ty, info, j0);
+  leaf_chol_block<6>(t, col, dinv, tx, ty, info, j0);
+  leaf_chol_block<7>(t, col, dinv, tx, ty, info, j0);
+  __syncthreads();   // dinv complete; col buffers free
+  leaf_inv_block<0>(t, col, dinv, tx, ty);
+  leaf_inv_block<1>(t, col, dinv, tx, ty);
+  leaf_inv_block<2>(t, col, dinv, tx, ty);
+  leaf_inv_block<3>(t, col, dinv, tx, ty);
+  leaf_inv_block<4>(t, col, dinv, tx, ty);
+  leaf_inv_block<5>(t, col, dinv, tx, ty);
+  leaf_inv_block<6>(t, col, dinv, tx, ty);
+  leaf_inv_block<7>(t, col, dinv, tx, ty);
+  // stage the packed matrix, then write L and W with coalesced rows
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) S[(ty + LT * a) * LEAF_LD + tx + LT * b] = t[a][b];
   __syncthreads();
   for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
-    int i = idx >> 7, j = idx & 127;
+    const int i = idx >> 7, j = idx & 127;
     double l, w;
     if (j < i) {
       l = S[i * LEAF_LD + j];
-      w = S[j * LEAF_LD + i];
+      w = -dinv[i] * S[j * LEAF_LD + i];   // W[i][j] = -acc(j,i) / L[i][i]
     } else if (j == i) {
-      l = dsq[i];
+      l = S[i * LEAF_LD + i];
       w = dinv[i];
     } else {
       l = 0.0;
@@ -89,11 +155,42 @@ __global__ void __launch_bounds__(256, 1)
   }
 }
 
+template <class T>
+int tile_count(const dg::GemmParams& p) {
+  const int tm = p.M / T::BM, tn = p.N / T::BN;
+  return p.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+}
+
+// Narrow GEMMs (fewer 128x128 tiles than SMs) sit on the critical path of the recursion: run them
+// with 64x64 tiles so that four times as many SMs share the work.
 template <bool A_KC, bool B_KC>
-int launch_gemm(mfgp_ctx* h, const dg::GemmParams& p) {
-  int tiles = p.lower_only ? p.tiles_m * (p.tiles_m + 1) / 2 : p.tiles_m * p.tiles_n;
-  if (tiles <= 0) return 0;
-  dg::gemm_kernel<A_KC, B_KC><<<tiles, dg::THREADS, dg::SMEM_BYTES, h->stream>>>(p);
+int launch_gemm(mfgp_ctx* h, const dg::GemmParams& p, int cls = PC_GEMM) {
+  const int big_tiles = tile_count<dg::Big>(p);
+  if (big_tiles <= 0) return 0;
+  prof_begin(h, cls);
+  if (big_tiles < MFGP_NUM_SMS) {
+    dg::gemm_kernel<dg::Small, A_KC, B_KC>
+        <<<tile_count<dg::Small>(p), dg::Small::THREADS, dg::Small::SMEM_BYTES, h->stream>>>(p);
+  } else {
+    dg::gemm_kernel<dg::Big, A_KC, B_KC>
+        <<<big_tiles, dg::Big::THREADS, dg::Big::SMEM_BYTES, h->stream>>>(p);
+  }
+  prof_end(h, cls);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+// X <- X * Wl^T in place (X: m x 128, Wl: 128 x 128): every CTA must own all 128 columns of its rows
+int launch_trsm_leaf(mfgp_ctx* h, const dg::GemmParams& p) {
+  prof_begin(h, PC_GEMM);
+  if (p.M / 128 < MFGP_NUM_SMS) {
+    dg::gemm_kernel<dg::Row32, true, true>
+        <<<tile_count<dg::Row32>(p), dg::Row32::THREADS, dg::Row32::SMEM_BYTES, h->stream>>>(p);
+  } else {
+    dg::gemm_kernel<dg::Big, true, true>
+        <<<tile_count<dg::Big>(p), dg::Big::THREADS, dg::Big::SMEM_BYTES, h->stream>>>(p);
+  }
+  prof_end(h, PC_GEMM);
   LAUNCH_CHECK(h);
   return 0;
 }
@@ -103,7 +200,7 @@ dg::GemmParams gp(const double* A, long lda, const double* B, long ldb, double* 
   dg::GemmParams p;
   memset(&p, 0, sizeof(p));
   p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
-  p.tiles_m = m / dg::BM; p.tiles_n = n / dg::BN; p.K = k;
+  p.M = m; p.N = n; p.K = k;
   p.alpha = alpha; p.beta = beta;
   return p;
 }
@@ -116,7 +213,7 @@ int trsm_rec(mfgp_ctx* h, double* A, double* W, long ld, int r0, int m, int j0, 
     double* X = A + (long)r0 * ld + j0;
     const double* Wl = W + (long)j0 * ld + j0;
     // X[r][c] = sum_k X[r][k] * Wl[c][k]; in place is safe: a CTA owns all 128 columns of its rows
-    return launch_gemm<true, true>(h, gp(X, ld, Wl, ld, X, ld, m, LEAF, LEAF, 1.0, 0.0));
+    return launch_trsm_leaf(h, gp(X, ld, Wl, ld, X, ld, m, LEAF, LEAF, 1.0, 0.0));
   }
   int n1 = split(n), n2 = n - n1, rc;
   if ((rc = trsm_rec(h, A, W, ld, r0, m, j0, n1))) return rc;
@@ -130,8 +227,10 @@ int trsm_rec(mfgp_ctx* h, double* A, double* W, long ld, int r0, int m, int j0, 
 int potrf_rec(mfgp_ctx* h, double* A, double* W, long ld, int j0, int n) {
   if (n == LEAF) {
     const int smem = LEAF * LEAF_LD * 8;
+    prof_begin(h, PC_LEAF);
     leaf_potrf_inv_kernel<<<1, 256, smem, h->stream>>>(A + (long)j0 * ld + j0, ld,
                                                        W + (long)j0 * ld + j0, ld, h->d_info, j0);
+    prof_end(h, PC_LEAF);
     LAUNCH_CHECK(h);
     return 0;
   }
@@ -175,15 +274,25 @@ int trtri_rec(mfgp_ctx* h, const double* L, double* W, long ld, int j0, int n) {
 
 }  // namespace
 
+template <class T, bool A_KC, bool B_KC>
+static int configure_gemm(mfgp_ctx* h) {
+  CUDA_TRY(h, cudaFuncSetAttribute(dg::gemm_kernel<T, A_KC, B_KC>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES));
+  return 0;
+}
+
 int linalg_configure(mfgp_ctx* h) {
-  CUDA_TRY(h, cudaFuncSetAttribute(dg::gemm_kernel<true, true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
-  CUDA_TRY(h, cudaFuncSetAttribute(dg::gemm_kernel<false, true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
-  CUDA_TRY(h, cudaFuncSetAttribute(dg::gemm_kernel<false, false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
+  int rc = 0;
+  rc |= configure_gemm<dg::Big, true, true>(h);
+  rc |= configure_gemm<dg::Big, false, true>(h);
+  rc |= configure_gemm<dg::Big, false, false>(h);
+  rc |= configure_gemm<dg::Small, true, true>(h);
+  rc |= configure_gemm<dg::Small, false, true>(h);
+  rc |= configure_gemm<dg::Small, false, false>(h);
+  rc |= configure_gemm<dg::Row32, true, true>(h);
+  if (rc) return -100;
   CUDA_TRY(h, cudaFuncSetAttribute(dg::trmm_sumsq_kernel,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::SMEM_BYTES));
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::Big::SMEM_BYTES));
   CUDA_TRY(h, cudaFuncSetAttribute(leaf_potrf_inv_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF * LEAF_LD * 8));
   return 0;
@@ -206,15 +315,17 @@ int lauum_padded(mfgp_ctx* h, const double* W, double* Kinv, int npad) {
   dg::GemmParams p = gp(W, npad, W, npad, Kinv, npad, npad, npad, npad, 1.0, 0.0);
   p.lower_only = 1;
   p.kb_row = 1;
-  return launch_gemm<false, false>(h, p);
+  return launch_gemm<false, false>(h, p, PC_LAUUM);
 }
 
 int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad,
                double* out_ss) {
-  ARG_CHECK(h, npad % LEAF == 0 && cols_pad % dg::BN == 0);
+  ARG_CHECK(h, npad % LEAF == 0 && cols_pad % dg::Big::BN == 0);
   if (cols_pad == 0) return 0;
-  dg::trmm_sumsq_kernel<<<(unsigned)(cols_pad / dg::BN), dg::THREADS, dg::SMEM_BYTES, h->stream>>>(
+  prof_begin(h, PC_TRMM_SUMSQ);
+  dg::trmm_sumsq_kernel<<<(unsigned)(cols_pad / dg::Big::BN), dg::Big::THREADS, dg::Big::SMEM_BYTES, h->stream>>>(
       W, npad, Ks, out_ss);
+  prof_end(h, PC_TRMM_SUMSQ);
   LAUNCH_CHECK(h);
   return 0;
 }

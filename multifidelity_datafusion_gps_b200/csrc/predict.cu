@@ -358,8 +358,10 @@ int cross_gen_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int
                      const double* alpha, const double* Xq, long long ncols, long long cols_pad,
                      double* Ks, double* mean) {
   if (cols_pad <= 0) return 0;
+  prof_begin(h, PC_CROSSGEN);
   cross_gen_kernel<<<nblk(cols_pad, 8), 256, 0, h->stream>>>(kp, X, N, npad, alpha, Xq, ncols,
                                                              cols_pad, Ks, mean);
+  prof_end(h, PC_CROSSGEN);
   LAUNCH_CHECK(h);
   return 0;
 }

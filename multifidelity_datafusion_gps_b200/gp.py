@@ -135,7 +135,7 @@ def to_device(arr, device):
     """numpy (host) -> contiguous float64 CUDA tensor through pinned memory."""
     a = np.ascontiguousarray(arr, dtype=np.float64)
     t = torch.from_numpy(a)
-    if a.size >= 1 << 16:
+    if a.size >= 1 << 16 and not t.is_pinned():     # callers may hand in views of pinned buffers
         t = t.pin_memory()
     return t.to("cuda:%d" % device, non_blocking=False)
 
