@@ -19,6 +19,12 @@ int fill_normal_launch(mfgp_ctx* h, unsigned long long seed, long long first, lo
 int build_mc_rows_launch(mfgp_ctx* h, const double* Xtest, const double* mu_l, const double* sd_l,
                          const double* eps, unsigned long long seed, long long m_global0,
                          long long m_lo, long long ncols, int S, int d, double* out);
+int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int npad,
+                        const double* alpha, const double* Xtest, const double* mu_l,
+                        const double* sd_l, const double* eps, unsigned long long seed,
+                        long long m_global0, long long m_lo, long long npts, int S,
+                        long long cols_pad, double* Ks, double* mu_c);
+int mc_max_samples();
 int sqrt_launch(mfgp_ctx* h, double* v, long long n);
 int mc_aggregate_launch(mfgp_ctx* h, const double* mu_c, const double* v_c, long long npts, int S,
                         double* mean, double* var);
@@ -439,10 +445,17 @@ int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t*
     const long long npts = (M - m_lo < pm) ? (M - m_lo) : pm;
     const long long ncols = npts * S;
     const long long cols_pad = (ncols + 127) / 128 * 128;
-    if ((rc = build_mc_rows_launch(h, d_Xtest, mu_l, sd_l, d_eps, seed, m0, m_lo, ncols, S, d, Xq)))
-      return rc;
-    if ((rc = cross_gen_launch(h, kh, hf->d_X, hf->N, npad, hf->d_alpha, Xq, ncols, cols_pad, Ks, mu_c)))
-      return rc;
+    if (S <= mc_max_samples()) {
+      // one CTA per test point: x-dependent kernel factors shared by its S samples (1 exp / element)
+      if ((rc = cross_gen_mc_launch(h, kh, hf->d_X, hf->N, npad, hf->d_alpha, d_Xtest, mu_l, sd_l, d_eps,
+                                    seed, m0, m_lo, npts, S, cols_pad, Ks, mu_c)))
+        return rc;
+    } else {
+      if ((rc = build_mc_rows_launch(h, d_Xtest, mu_l, sd_l, d_eps, seed, m0, m_lo, ncols, S, d, Xq)))
+        return rc;
+      if ((rc = cross_gen_launch(h, kh, hf->d_X, hf->N, npad, hf->d_alpha, Xq, ncols, cols_pad, Ks, mu_c)))
+        return rc;
+    }
     if ((rc = trmm_sumsq(h, hf->d_W, npad, Ks, cols_pad, ss))) return rc;
     if ((rc = finish_var_launch(h, ss, ncols, kh.kdiag, include_hf_noise ? kh.noise : 0.0, ss)))
       return rc;

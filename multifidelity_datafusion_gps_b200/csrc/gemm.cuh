@@ -216,21 +216,98 @@ __global__ void __launch_bounds__(Big::THREADS, 1)
 #pragma unroll
   for (int j = 0; j < T::NT; j++) ss[j][0] = ss[j][1] = 0.0;
 
-  for (int ti = 0; ti < npad / T::BM; ti++) {
-    double acc[T::MT][T::NT][2];
+  // One flattened software pipeline over all (row tile, k tile) pairs: row tile ti needs the k tiles
+  // 0 .. 8(ti+1)-1, the loads of the next row tile are already in flight while the current one is
+  // finished, and inside the diagonal 128x128 block of W the 8-row DMMA tiles that lie entirely
+  // above the diagonal (explicit zeros) are skipped -- adding 0*b is exact, so this changes no bit.
+  const int tid = threadIdx.x;
+  const int wm0 = (warp / T::WGN) * T::WTM;
+  const int nrt = npad / T::BM;
+  const int total = 4 * nrt * (nrt + 1);          // sum over ti of 8 (ti + 1) k tiles
+  constexpr int KT_PER_TILE = T::BM / BK;         // 8
+  int l_ti = 0, l_kt = 0;                         // loader position
+  auto issue_load = [&](int stage) {
+    double* sa = smem + stage * T::STAGE_DOUBLES;
+    load_operand<true, T::BM, T::THREADS>(sa, W, npad, l_ti * T::BM, l_kt * BK, tid);
+    load_operand<true, T::BN, T::THREADS>(sa + T::A_STAGE, Ks, npad, col0, l_kt * BK, tid);
+    if (++l_kt == KT_PER_TILE * (l_ti + 1)) { l_kt = 0; ++l_ti; }
+  };
 #pragma unroll
-    for (int i = 0; i < T::MT; i++)
-#pragma unroll
-      for (int j = 0; j < T::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    mainloop<T, true, true>(acc, W, npad, Ks, npad, ti * T::BM, col0, 0, ti * T::BM + T::BM, smem);
-#pragma unroll
-    for (int i = 0; i < T::MT; i++)
-#pragma unroll
-      for (int j = 0; j < T::NT; j++) {
-        ss[j][0] = fma(acc[i][j][0], acc[i][j][0], ss[j][0]);
-        ss[j][1] = fma(acc[i][j][1], acc[i][j][1], ss[j][1]);
-      }
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (s < total) issue_load(s);
+    cp_async_commit();
   }
+  double acc[T::MT][T::NT][2];
+#pragma unroll
+  for (int i = 0; i < T::MT; i++)
+#pragma unroll
+    for (int j = 0; j < T::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  int c_ti = 0, c_kt = 0;                         // consumer position
+  for (int f = 0; f < total; f++) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (f + STAGES - 1 < total) issue_load((f + STAGES - 1) % STAGES);
+    cp_async_commit();
+    const double* sa = smem + (f % STAGES) * T::STAGE_DOUBLES;
+    const double* sb = sa + T::A_STAGE;
+    const int krel = c_kt * BK - c_ti * T::BM;    // >= 0 inside the diagonal block
+    if (krel < 0) {                               // dense part of the row tile: no zero structure
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; kk++) {
+        double a[T::MT], b[T::NT];
+#pragma unroll
+        for (int i = 0; i < T::MT; i++) a[i] = sa[(wm0 + 8 * i + g) * KC_STRIDE + kk * 4 + t];
+#pragma unroll
+        for (int j = 0; j < T::NT; j++) b[j] = sb[(wn0 + 8 * j + g) * KC_STRIDE + kk * 4 + t];
+#pragma unroll
+        for (int i = 0; i < T::MT; i++)
+#pragma unroll
+          for (int j = 0; j < T::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    } else {
+      // Diagonal block.  The skipped tiles must not even be issued (a predicated-off DMMA still
+      // occupies the tensor pipe), hence a warp-uniform computed entry into a fall-through chain.
+      static_assert(T::MT == 8, "fall-through chain below is written for 8 row tiles per warp");
+#pragma unroll 1
+      for (int kk = 0; kk < BK / 4; kk++) {
+        const int imin = max(0, (krel + 4 * kk - wm0) >> 3);
+        if (imin >= T::MT) break;                 // later kk only skip more
+        double b[T::NT];
+#pragma unroll
+        for (int j = 0; j < T::NT; j++) b[j] = sb[(wn0 + 8 * j + g) * KC_STRIDE + kk * 4 + t];
+#define MFGP_ROWTILE(i)                                                              \
+  {                                                                                  \
+    const double a_ = sa[(wm0 + 8 * (i) + g) * KC_STRIDE + kk * 4 + t];              \
+    _Pragma("unroll") for (int j = 0; j < T::NT; j++)                                \
+        dmma884(acc[i][j][0], acc[i][j][1], a_, b[j]);                               \
+  }
+        switch (imin) {
+          case 0: MFGP_ROWTILE(0)
+          case 1: MFGP_ROWTILE(1)
+          case 2: MFGP_ROWTILE(2)
+          case 3: MFGP_ROWTILE(3)
+          case 4: MFGP_ROWTILE(4)
+          case 5: MFGP_ROWTILE(5)
+          case 6: MFGP_ROWTILE(6)
+          default: MFGP_ROWTILE(7)
+        }
+#undef MFGP_ROWTILE
+      }
+    }
+    if (++c_kt == KT_PER_TILE * (c_ti + 1)) {     // row tile finished: fold its rows into the sums
+#pragma unroll
+      for (int i = 0; i < T::MT; i++)
+#pragma unroll
+        for (int j = 0; j < T::NT; j++) {
+          ss[j][0] = fma(acc[i][j][0], acc[i][j][0], ss[j][0]);
+          ss[j][1] = fma(acc[i][j][1], acc[i][j][1], ss[j][1]);
+          acc[i][j][0] = acc[i][j][1] = 0.0;
+        }
+      c_kt = 0;
+      ++c_ti;
+    }
+  }
+  cp_async_wait<0>();
   // reduce over the 8 row groups g (lanes with equal t), then over the two warp rows
 #pragma unroll
   for (int j = 0; j < T::NT; j++)

@@ -55,6 +55,52 @@ __global__ void __launch_bounds__(256)
   if (lane == 0 && mean) mean[c] = acc;
 }
 
+// Same contract, input width known at compile time: the query row lives in registers and the
+// distance loops are unrolled (the generic kernel spends most of its issue slots on local-memory
+// traffic and loop control: 183 instructions per element in ncu).
+template <int DT>
+__global__ void __launch_bounds__(256)
+    cross_gen_fixed_kernel(KParams kp, const double* __restrict__ X, int N, int npad,
+                           const double* __restrict__ alpha, const double* __restrict__ Xq,
+                           long long ncols, long long cols_pad, double* __restrict__ Ks,
+                           double* __restrict__ mean) {
+  const int lane = threadIdx.x & 31;
+  const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= cols_pad) return;
+  double* row = Ks ? Ks + c * npad : nullptr;
+  if (c >= ncols) {
+    if (row)
+      for (int k = lane; k < npad; k += 32) row[k] = 0.0;
+    return;
+  }
+  double q[DT];
+#pragma unroll
+  for (int dd = 0; dd < DT; dd++) q[dd] = Xq[c * DT + dd];
+  const int d = kp.d;
+  const bool has3 = kp.s3 != 0.0;
+  double acc = 0.0;
+  for (int k = lane; k < npad; k += 32) {
+    double v = 0.0;
+    if (k < N) {
+      const double* xk = X + (long)k * DT;
+      double rx = 0.0, rz = 0.0;
+#pragma unroll
+      for (int dd = 0; dd < DT; dd++) {
+        const double t = q[dd] - xk[dd];
+        if (dd < d) rx = fma(t, t, rx);
+        else rz = fma(t, t, rz);
+      }
+      v = kp.c12 * exp(fma(kp.az, rz, kp.ax * rx));
+      if (has3) v = fma(kp.s3, exp(kp.a3 * rx), v);
+      acc = fma(v, alpha[k], acc);
+    }
+    if (row) row[k] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && mean) mean[c] = acc;
+}
+
 __global__ void finish_var_kernel(const double* ss, long long n, double kdiag, double noise_add,
                                   double* var) {   // may run in place (ss == var)
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,6 +181,89 @@ __global__ void build_mc_rows_kernel(const double* __restrict__ Xtest, const dou
   double* row = out + c * (d + 1);
   for (int dd = 0; dd < d; dd++) row[dd] = Xtest[m * d + dd];
   row[d] = fma(sd_l[m], e, mu_l[m]);
+}
+
+// K7 generator: one CTA per test point m, all S samples of it.  Only k1(z_s, Z_k) depends on the
+// sample, so the x-dependent factors are computed once per (m, k) into shared memory
+//   su[k] = ax |x_m - X_k|^2,  sv[k] = s3 exp(a3 |x_m - X_k|^2),  sz[k] = Z_k,  sa[k] = alpha_k
+// and every (sample, k) element then costs ONE exponential:
+//   Ks[(m,s)][k] = c12 exp(az (z_s - Z_k)^2 + su[k]) + sv[k],   mu[(m,s)] = sum_k Ks alpha_k.
+// Columns are written with 16-byte stores; the per-sample mean is reduced in a fixed order.
+constexpr int MC_KCHUNK = 1024;   // k values staged per pass (4 arrays x 8 KB, static smem)
+constexpr int MC_MAXS = 1024;
+
+__global__ void __launch_bounds__(256)
+    cross_gen_mc_kernel(KParams kp, const double* __restrict__ X, int N, int npad,
+                        const double* __restrict__ alpha, const double* __restrict__ Xtest,
+                        const double* __restrict__ mu_l, const double* __restrict__ sd_l,
+                        const double* __restrict__ eps, unsigned long long seed, long long m_global0,
+                        long long m_lo, int S, double* __restrict__ Ks, double* __restrict__ mu_c) {
+  __shared__ __align__(16) double su[MC_KCHUNK], sv[MC_KCHUNK], sz[MC_KCHUNK], sa[MC_KCHUNK];
+  __shared__ double macc[MC_MAXS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long m = m_lo + blockIdx.x;
+  const int d = kp.d;               // D = d + 1
+  double xm[MFGP_MAX_D];
+  for (int dd = 0; dd < d; dd++) xm[dd] = Xtest[m * d + dd];
+  const double mul = mu_l[m], sdl = sd_l[m];
+  for (int s = tid; s < S; s += 256) macc[s] = 0.0;
+  for (int k0 = 0; k0 < npad; k0 += MC_KCHUNK) {
+    const int klen = min(MC_KCHUNK, npad - k0);
+    __syncthreads();
+    for (int kk = tid; kk < klen; kk += 256) {
+      const int k = k0 + kk;
+      if (k < N) {
+        const double* xk = X + (long)k * (d + 1);
+        double rx = 0.0;
+        for (int dd = 0; dd < d; dd++) {
+          const double t = xm[dd] - xk[dd];
+          rx = fma(t, t, rx);
+        }
+        su[kk] = kp.ax * rx;
+        sv[kk] = kp.s3 != 0.0 ? kp.s3 * exp(kp.a3 * rx) : 0.0;
+        sz[kk] = xk[d];
+        sa[kk] = alpha[k];
+      } else {   // pad: exp(-inf) = 0 -> the element is exactly 0
+        su[kk] = -INFINITY;
+        sv[kk] = 0.0;
+        sz[kk] = 0.0;
+        sa[kk] = 0.0;
+      }
+    }
+    __syncthreads();
+    for (int s = warp; s < S; s += 8) {
+      double e = 0.0;
+      if (lane == 0)
+        e = eps ? eps[m * S + s] : philox_normal((unsigned long long)((m_global0 + m) * S + s), seed);
+      e = __shfl_sync(0xffffffffu, e, 0);
+      const double z = fma(sdl, e, mul);
+      double* row = Ks + ((long long)blockIdx.x * S + s) * npad + k0;
+      double acc = 0.0;
+      for (int kk = 2 * lane; kk < klen; kk += 64) {
+        const double2 u = *reinterpret_cast<const double2*>(su + kk);
+        const double2 v = *reinterpret_cast<const double2*>(sv + kk);
+        const double2 zz = *reinterpret_cast<const double2*>(sz + kk);
+        const double2 a = *reinterpret_cast<const double2*>(sa + kk);
+        const double t0 = z - zz.x, t1 = z - zz.y;
+        double2 o;
+        o.x = fma(kp.c12, exp(fma(kp.az * t0, t0, u.x)), v.x);
+        o.y = fma(kp.c12, exp(fma(kp.az * t1, t1, u.y)), v.y);
+        *reinterpret_cast<double2*>(row + kk) = o;
+        acc = fma(o.x, a.x, acc);
+        acc = fma(o.y, a.y, acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) macc[s] += acc;   // warp `s % 8` is the only writer of macc[s]
+    }
+  }
+  __syncthreads();
+  for (int s = tid; s < S; s += 256) mu_c[(long long)blockIdx.x * S + s] = macc[s];
+}
+
+__global__ void zero_rows_kernel(double* __restrict__ p, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
 }
 
 __global__ void sqrt_kernel(double* __restrict__ v, long long n) {
@@ -358,13 +487,48 @@ int cross_gen_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int
                      const double* alpha, const double* Xq, long long ncols, long long cols_pad,
                      double* Ks, double* mean) {
   if (cols_pad <= 0) return 0;
+  const unsigned grid = nblk(cols_pad, 8);
   prof_begin(h, PC_CROSSGEN);
-  cross_gen_kernel<<<nblk(cols_pad, 8), 256, 0, h->stream>>>(kp, X, N, npad, alpha, Xq, ncols,
-                                                             cols_pad, Ks, mean);
+#define MFGP_XGEN(DT)                                                                              \
+  case DT:                                                                                         \
+    cross_gen_fixed_kernel<DT><<<grid, 256, 0, h->stream>>>(kp, X, N, npad, alpha, Xq, ncols,      \
+                                                            cols_pad, Ks, mean);                   \
+    break;
+  switch (kp.D) {
+    MFGP_XGEN(1) MFGP_XGEN(2) MFGP_XGEN(3) MFGP_XGEN(4) MFGP_XGEN(5) MFGP_XGEN(6) MFGP_XGEN(7)
+    MFGP_XGEN(8) MFGP_XGEN(9) MFGP_XGEN(10) MFGP_XGEN(11) MFGP_XGEN(12) MFGP_XGEN(13)
+    default:
+      cross_gen_kernel<<<grid, 256, 0, h->stream>>>(kp, X, N, npad, alpha, Xq, ncols, cols_pad, Ks,
+                                                    mean);
+  }
+#undef MFGP_XGEN
   prof_end(h, PC_CROSSGEN);
   LAUNCH_CHECK(h);
   return 0;
 }
+
+// K7 generator for npts test points x S samples starting at point m_lo; zero-fills the pad columns
+int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int npad,
+                        const double* alpha, const double* Xtest, const double* mu_l,
+                        const double* sd_l, const double* eps, unsigned long long seed,
+                        long long m_global0, long long m_lo, long long npts, int S,
+                        long long cols_pad, double* Ks, double* mu_c) {
+  if (npts <= 0) return 0;
+  ARG_CHECK(h, S <= MC_MAXS);
+  prof_begin(h, PC_CROSSGEN);
+  cross_gen_mc_kernel<<<(unsigned)npts, 256, 0, h->stream>>>(kp, X, N, npad, alpha, Xtest, mu_l, sd_l,
+                                                             eps, seed, m_global0, m_lo, S, Ks, mu_c);
+  prof_end(h, PC_CROSSGEN);
+  LAUNCH_CHECK(h);
+  const long long tail = (cols_pad - npts * S) * npad;
+  if (tail > 0) {
+    zero_rows_kernel<<<nblk(tail, 256), 256, 0, h->stream>>>(Ks + npts * S * npad, tail);
+    LAUNCH_CHECK(h);
+  }
+  return 0;
+}
+
+int mc_max_samples() { return MC_MAXS; }
 
 int finish_var_launch(mfgp_ctx* h, const double* ss, long long n, double kdiag, double noise_add,
                       double* var) {
