@@ -248,8 +248,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--nh", type=int, default=1024)
     ap.add_argument("--nl", type=int, default=4096)
-    ap.add_argument("--m", type=int, default=32 ** 4)
-    ap.add_argument("--s", type=int, default=100)
+    # (--points / --samples rather than --m / --s: torchrun's own parser treats "--m" as ambiguous)
+    ap.add_argument("--points", "--m", dest="m", type=int, default=32 ** 4)
+    ap.add_argument("--samples", "--s", dest="s", type=int, default=100)
     ap.add_argument("--ref-points", type=int, default=1024, dest="ref_points")
     ap.add_argument("--cpu-points", type=int, default=1024, dest="cpu_points")
     ap.add_argument("--no-lml", action="store_true")
