@@ -4,7 +4,9 @@
 // RBF(z)*RBF(x) + RBF(x)) plus GPy's diag.add(Ky, noise + 1e-8): one fused pass, no N x N
 // temporaries (GPy materialises three distance matrices and ~6 elementwise temporaries).
 // The product k1*k2 is folded into a single exponential, so a composite element costs two exps.
-// HBM-bound by design: 8 bytes written per element, inputs (N x D) stay in L1/shared memory.
+// HBM-bound by contract (8 bytes written per element, inputs (N x D) stay in shared memory), but on
+// B200 the FP64 pipe is the tighter bound for the exponentials; fastmath.cuh's exp_neg (10 FP64
+// instructions + one table lookup) is what keeps the kernel near the memory roofline.
 //
 // K5 replaces GPy's update_gradients_full chain (stationary.py / prod.py / add.py) for
 // dL_dK = 0.5 (alpha alpha^T - K^-1): one streaming pass over K^-1's lower triangle that
@@ -12,6 +14,7 @@
 //   S0 = sum G K12, S1 = sum G K12 rz2, S2 = sum G K12 rx2, S3 = sum G K3, S4 = sum G K3 rx2, S5 = tr G
 // in a fixed order (persistent blocks, fixed tile->block map, two-stage reduction).
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace {
 
@@ -33,12 +36,47 @@ __device__ __forceinline__ void load_rows(double* sX, const double* X, int N, in
   }
 }
 
+// squared distances of the thread's 4x4 sub-block: rows ty+16i, columns 4tx+j
+__device__ __forceinline__ void sub_block_dist(const double* sXi, const double* sXj, int D, int d, int tx,
+                                               int ty, double (&rx)[4][4], double (&rz)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) rx[i][j] = rz[i][j] = 0.0;
+  for (int dd = 0; dd < D; dd++) {
+    double xi[4], xj[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) xi[i] = sXi[dd * AT + ty + 16 * i];          // broadcast within a half-warp
+    const double2 p0 = *reinterpret_cast<const double2*>(sXj + dd * AT + 4 * tx);   // 16-byte loads: no conflicts
+    const double2 p1 = *reinterpret_cast<const double2*>(sXj + dd * AT + 4 * tx + 2);
+    xj[0] = p0.x; xj[1] = p0.y; xj[2] = p1.x; xj[3] = p1.y;
+    if (dd < d) {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const double t = xi[i] - xj[j];
+          rx[i][j] = fma(t, t, rx[i][j]);
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const double t = xi[i] - xj[j];
+          rz[i][j] = fma(t, t, rz[i][j]);
+        }
+    }
+  }
+}
+
 template <bool VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     assemble_kernel(KParams kp, const double* __restrict__ X, int N, double diag_add,
                     double* __restrict__ K, long ldk, int lower_only, int tiles, int nrows) {
-  __shared__ double sXi[MFGP_MAX_D * AT];
-  __shared__ double sXj[MFGP_MAX_D * AT];
+  __shared__ __align__(16) double sXi[MFGP_MAX_D * AT];
+  __shared__ __align__(16) double sXj[MFGP_MAX_D * AT];
+  __shared__ double stbl[64];
   int ti, tj;
   if (lower_only) {
     tile_from_linear(blockIdx.x, ti, tj);
@@ -48,39 +86,13 @@ __global__ void __launch_bounds__(256)
   }
   const int row0 = ti * AT, col0 = tj * AT;
   const int D = kp.D, d = kp.d;
+  fm::load_exp_table(stbl);
   load_rows(sXi, X, N, D, row0);
   load_rows(sXj, X, N, D, col0);
   __syncthreads();
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   double rx[4][4], rz[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) rx[i][j] = rz[i][j] = 0.0;
-  for (int dd = 0; dd < D; dd++) {
-    double xi[4], xj[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) xi[i] = sXi[dd * AT + ty + 16 * i];
-#pragma unroll
-    for (int j = 0; j < 4; j++) xj[j] = sXj[dd * AT + 4 * tx + j];
-    if (dd < d) {
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          double t = xi[i] - xj[j];
-          rx[i][j] = fma(t, t, rx[i][j]);
-        }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          double t = xi[i] - xj[j];
-          rz[i][j] = fma(t, t, rz[i][j]);
-        }
-    }
-  }
+  sub_block_dist(sXi, sXj, D, d, tx, ty, rx, rz);
   const bool has3 = kp.s3 != 0.0;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -92,8 +104,8 @@ __global__ void __launch_bounds__(256)
       const int c = col0 + 4 * tx + j;
       double val;
       if (r < N && c < N) {
-        val = kp.c12 * exp(fma(kp.az, rz[i][j], kp.ax * rx[i][j]));
-        if (has3) val = fma(kp.s3, exp(kp.a3 * rx[i][j]), val);
+        val = kp.c12 * fm::exp_neg(fma(kp.az, rz[i][j], kp.ax * rx[i][j]), stbl);
+        if (has3) val = fma(kp.s3, fm::exp_neg(kp.a3 * rx[i][j], stbl), val);
         if (r == c) val += diag_add;
       } else {
         val = (r == c) ? 1.0 : 0.0;   // identity pad block
@@ -115,17 +127,19 @@ __global__ void __launch_bounds__(256)
 
 constexpr int GR_BLOCKS = MFGP_NUM_SMS * 4;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
     grad_reduce_kernel(KParams kp, const double* __restrict__ X, int N,
                        const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
                        int ntiles_lin, double* __restrict__ partials) {
-  __shared__ double sXi[MFGP_MAX_D * AT];
-  __shared__ double sXj[MFGP_MAX_D * AT];
-  __shared__ double sAi[AT], sAj[AT];
+  __shared__ __align__(16) double sXi[MFGP_MAX_D * AT];
+  __shared__ __align__(16) double sXj[MFGP_MAX_D * AT];
+  __shared__ __align__(16) double sAi[AT], sAj[AT];
   __shared__ double red[8][6];
+  __shared__ double stbl[64];
   const int D = kp.D, d = kp.d;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const bool has3 = kp.s3 != 0.0;
+  fm::load_exp_table(stbl);
   double S[6] = {0, 0, 0, 0, 0, 0};
   for (int tt = blockIdx.x; tt < ntiles_lin; tt += gridDim.x) {
     int ti, tj;
@@ -142,56 +156,42 @@ __global__ void __launch_bounds__(256)
       sAj[threadIdx.x - AT] = c < N ? alpha[c] : 0.0;
     }
     __syncthreads();
-    double rx[4][4], rz[4][4];
+    // issue the K^-1 loads first so that they overlap the distance computation
+    double kin[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) rx[i][j] = rz[i][j] = 0.0;
-    for (int dd = 0; dd < D; dd++) {
-      double xi[4], xj[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) xi[i] = sXi[dd * AT + ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 4; j++) xj[j] = sXj[dd * AT + 4 * tx + j];
-      if (dd < d) {
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            double t = xi[i] - xj[j];
-            rx[i][j] = fma(t, t, rx[i][j]);
-          }
+    for (int i = 0; i < 4; i++) {
+      const int r = row0 + ty + 16 * i;
+      if (r < N) {
+        const double2* src = reinterpret_cast<const double2*>(Kinv + (long)r * ld + col0 + 4 * tx);
+        const double2 q0 = src[0], q1 = src[1];
+        kin[i][0] = q0.x; kin[i][1] = q0.y; kin[i][2] = q1.x; kin[i][3] = q1.y;
       } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            double t = xi[i] - xj[j];
-            rz[i][j] = fma(t, t, rz[i][j]);
-          }
+        kin[i][0] = kin[i][1] = kin[i][2] = kin[i][3] = 0.0;
       }
     }
+    double rx[4][4], rz[4][4];
+    sub_block_dist(sXi, sXj, D, d, tx, ty, rx, rz);
+    const double2 a0 = *reinterpret_cast<const double2*>(sAj + 4 * tx);
+    const double2 a1 = *reinterpret_cast<const double2*>(sAj + 4 * tx + 2);
+    const double aj[4] = {a0.x, a0.y, a1.x, a1.y};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int r = row0 + ty + 16 * i;
       if (r >= N) continue;
-      const double2* src = reinterpret_cast<const double2*>(Kinv + (long)r * ld + col0 + 4 * tx);
-      double2 q0 = src[0], q1 = src[1];
-      double kin[4] = {q0.x, q0.y, q1.x, q1.y};
       const double ai = sAi[ty + 16 * i];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int c = col0 + 4 * tx + j;
         if (c > r || c >= N) continue;
         const double w = (c == r) ? 0.5 : 1.0;   // G = 0.5(aa^T - Kinv); off-diagonal counted twice
-        const double G = w * (ai * sAj[4 * tx + j] - kin[j]);
-        const double k12 = kp.c12 * exp(fma(kp.az, rz[i][j], kp.ax * rx[i][j]));
+        const double G = w * (ai * aj[j] - kin[i][j]);
+        const double k12 = kp.c12 * fm::exp_neg(fma(kp.az, rz[i][j], kp.ax * rx[i][j]), stbl);
         const double gk = G * k12;
         S[0] += gk;
         S[1] = fma(gk, rz[i][j], S[1]);
         S[2] = fma(gk, rx[i][j], S[2]);
         if (has3) {
-          const double g3 = G * kp.s3 * exp(kp.a3 * rx[i][j]);
+          const double g3 = G * kp.s3 * fm::exp_neg(kp.a3 * rx[i][j], stbl);
           S[3] += g3;
           S[4] = fma(g3, rx[i][j], S[4]);
         }

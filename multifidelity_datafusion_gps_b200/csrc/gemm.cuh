@@ -37,6 +37,7 @@ struct TileCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_DOUBLES * 8;
 };
 using Big = TileCfg<128, 128, 2, 4>;     // 163840 B smem
+using Big16 = TileCfg<128, 128, 4, 4>;   // same tile, 16 warps of 32x32 (4 warps per scheduler)
 using Small = TileCfg<64, 64, 2, 2>;     //  81920 B smem
 using Row32 = TileCfg<32, 128, 1, 4>;    // 102400 B smem: owns all 128 columns of its 32 rows (in-place TRSM leaf)
 
@@ -103,15 +104,6 @@ __device__ __forceinline__ void mainloop(double (&acc)[T::MT][T::NT][2], const d
   for (int kt = 0; kt < nk; kt++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    {
-      int nxt = kt + STAGES - 1;
-      if (nxt < nk) {
-        double* sa = smem + (nxt % STAGES) * T::STAGE_DOUBLES;
-        load_operand<A_KC, T::BM, T::THREADS>(sa, A, lda, row0, k_begin + nxt * BK, tid);
-        load_operand<B_KC, T::BN, T::THREADS>(sa + T::A_STAGE, B, ldb, col0, k_begin + nxt * BK, tid);
-      }
-      cp_async_commit();
-    }
     const double* sa = smem + (kt % STAGES) * T::STAGE_DOUBLES;
     const double* sb = sa + T::A_STAGE;
 #pragma unroll
@@ -129,6 +121,17 @@ __device__ __forceinline__ void mainloop(double (&acc)[T::MT][T::NT][2], const d
       for (int i = 0; i < T::MT; i++)
 #pragma unroll
         for (int j = 0; j < T::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      if (kk == 0) {
+        // refill the stage freed by the previous k tile only now: the first DMMAs are already
+        // queued, so the tensor pipe does not drain while the copies are being issued
+        int nxt = kt + STAGES - 1;
+        if (nxt < nk) {
+          double* sn = smem + (nxt % STAGES) * T::STAGE_DOUBLES;
+          load_operand<A_KC, T::BM, T::THREADS>(sn, A, lda, row0, k_begin + nxt * BK, tid);
+          load_operand<B_KC, T::BN, T::THREADS>(sn + T::A_STAGE, B, ldb, col0, k_begin + nxt * BK, tid);
+        }
+        cp_async_commit();
+      }
     }
   }
   cp_async_wait<0>();
@@ -203,11 +206,11 @@ __global__ void __launch_bounds__(T::THREADS) gemm_kernel(GemmParams p) {
 // tmp = W * Ks^T with fused column sum of squares; one CTA owns a 128-column tile of Ks and walks
 // all row tiles of the lower-triangular W (k < row0+128), so the reduction order is fixed.
 //   out_ss[c] = sum_i ( sum_{k<=i} W[i][k] * Ks[c][k] )^2
-__global__ void __launch_bounds__(Big::THREADS, 1)
+template <class T>
+__global__ void __launch_bounds__(T::THREADS, 1)
     trmm_sumsq_kernel(const double* W, int npad, const double* Ks, double* out_ss) {
-  using T = Big;
   extern __shared__ __align__(16) double smem[];
-  __shared__ double red[2][T::BN];
+  __shared__ double red[T::WGM][T::BN];
   const int col0 = blockIdx.x * T::BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -246,8 +249,6 @@ __global__ void __launch_bounds__(Big::THREADS, 1)
   for (int f = 0; f < total; f++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
-    if (f + STAGES - 1 < total) issue_load((f + STAGES - 1) % STAGES);
-    cp_async_commit();
     const double* sa = smem + (f % STAGES) * T::STAGE_DOUBLES;
     const double* sb = sa + T::A_STAGE;
     const int krel = c_kt * BK - c_ti * T::BM;    // >= 0 inside the diagonal block
@@ -263,11 +264,17 @@ __global__ void __launch_bounds__(Big::THREADS, 1)
         for (int i = 0; i < T::MT; i++)
 #pragma unroll
           for (int j = 0; j < T::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        if (kk == 0) {                            // refill after the first DMMAs are queued
+          if (f + STAGES - 1 < total) issue_load((f + STAGES - 1) % STAGES);
+          cp_async_commit();
+        }
       }
     } else {
+      if (f + STAGES - 1 < total) issue_load((f + STAGES - 1) % STAGES);
+      cp_async_commit();
       // Diagonal block.  The skipped tiles must not even be issued (a predicated-off DMMA still
       // occupies the tensor pipe), hence a warp-uniform computed entry into a fall-through chain.
-      static_assert(T::MT == 8, "fall-through chain below is written for 8 row tiles per warp");
+      static_assert(T::MT <= 8, "fall-through chain below covers at most 8 row tiles per warp");
 #pragma unroll 1
       for (int kk = 0; kk < BK / 4; kk++) {
         const int imin = max(0, (krel + 4 * kk - wm0) >> 3);
@@ -276,10 +283,10 @@ __global__ void __launch_bounds__(Big::THREADS, 1)
 #pragma unroll
         for (int j = 0; j < T::NT; j++) b[j] = sb[(wn0 + 8 * j + g) * KC_STRIDE + kk * 4 + t];
 #define MFGP_ROWTILE(i)                                                              \
-  {                                                                                  \
+  if constexpr ((i) < T::MT) {                                                       \
     const double a_ = sa[(wm0 + 8 * (i) + g) * KC_STRIDE + kk * 4 + t];              \
     _Pragma("unroll") for (int j = 0; j < T::NT; j++)                                \
-        dmma884(acc[i][j][0], acc[i][j][1], a_, b[j]);                               \
+        dmma884(acc[(i) < T::MT ? (i) : 0][j][0], acc[(i) < T::MT ? (i) : 0][j][1], a_, b[j]); \
   }
         switch (imin) {
           case 0: MFGP_ROWTILE(0)
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(Big::THREADS, 1)
     }
   }
   cp_async_wait<0>();
-  // reduce over the 8 row groups g (lanes with equal t), then over the two warp rows
+  // reduce over the 8 row groups g (lanes with equal t), then over the warp rows (fixed order)
 #pragma unroll
   for (int j = 0; j < T::NT; j++)
 #pragma unroll
@@ -327,7 +334,12 @@ __global__ void __launch_bounds__(Big::THREADS, 1)
     }
   }
   __syncthreads();
-  if (threadIdx.x < T::BN) out_ss[col0 + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x];
+  if (threadIdx.x < T::BN) {
+    double v = red[0][threadIdx.x];
+#pragma unroll
+    for (int r = 1; r < T::WGM; r++) v += red[r][threadIdx.x];
+    out_ss[col0 + threadIdx.x] = v;
+  }
 }
 
 }  // namespace dg

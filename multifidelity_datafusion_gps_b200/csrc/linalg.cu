@@ -9,6 +9,7 @@
 //              inverse); A22 -= A21 A21^T (SYRK, lower tiles); potrf(A22)
 //   trtri(n):  trtri(11), trtri(22); W21 = -W22 L21 W11
 //   lauum:     Kinv = W^T W, one launch over the lower tiles with k >= row0
+#include <stdlib.h>
 #include "gemm.cuh"
 
 namespace {
@@ -155,6 +156,16 @@ __global__ void __launch_bounds__(256, 1)
   }
 }
 
+// A/B switch for the throughput tile (environment MFGP_TILE_WARPS=8|16), read once
+int tile_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFGP_TILE_WARPS");
+    v = (e && atoi(e) == 8) ? 8 : 16;
+  }
+  return v;
+}
+
 template <class T>
 int tile_count(const dg::GemmParams& p) {
   const int tm = p.M / T::BM, tn = p.N / T::BN;
@@ -171,6 +182,9 @@ int launch_gemm(mfgp_ctx* h, const dg::GemmParams& p, int cls = PC_GEMM) {
   if (big_tiles < MFGP_NUM_SMS) {
     dg::gemm_kernel<dg::Small, A_KC, B_KC>
         <<<tile_count<dg::Small>(p), dg::Small::THREADS, dg::Small::SMEM_BYTES, h->stream>>>(p);
+  } else if (tile_variant() == 16) {
+    dg::gemm_kernel<dg::Big16, A_KC, B_KC>
+        <<<big_tiles, dg::Big16::THREADS, dg::Big16::SMEM_BYTES, h->stream>>>(p);
   } else {
     dg::gemm_kernel<dg::Big, A_KC, B_KC>
         <<<big_tiles, dg::Big::THREADS, dg::Big::SMEM_BYTES, h->stream>>>(p);
@@ -291,8 +305,14 @@ int linalg_configure(mfgp_ctx* h) {
   rc |= configure_gemm<dg::Small, false, false>(h);
   rc |= configure_gemm<dg::Row32, true, true>(h);
   if (rc) return -100;
-  CUDA_TRY(h, cudaFuncSetAttribute(dg::trmm_sumsq_kernel,
+  CUDA_TRY(h, cudaFuncSetAttribute(dg::trmm_sumsq_kernel<dg::Big>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, dg::Big::SMEM_BYTES));
+  CUDA_TRY(h, cudaFuncSetAttribute(dg::trmm_sumsq_kernel<dg::Big16>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::Big16::SMEM_BYTES));
+  rc |= configure_gemm<dg::Big16, true, true>(h);
+  rc |= configure_gemm<dg::Big16, false, true>(h);
+  rc |= configure_gemm<dg::Big16, false, false>(h);
+  if (rc) return -100;
   CUDA_TRY(h, cudaFuncSetAttribute(leaf_potrf_inv_kernel,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF * LEAF_LD * 8));
   return 0;
@@ -323,8 +343,12 @@ int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long lo
   ARG_CHECK(h, npad % LEAF == 0 && cols_pad % dg::Big::BN == 0);
   if (cols_pad == 0) return 0;
   prof_begin(h, PC_TRMM_SUMSQ);
-  dg::trmm_sumsq_kernel<<<(unsigned)(cols_pad / dg::Big::BN), dg::Big::THREADS, dg::Big::SMEM_BYTES, h->stream>>>(
-      W, npad, Ks, out_ss);
+  if (tile_variant() == 16)
+    dg::trmm_sumsq_kernel<dg::Big16><<<(unsigned)(cols_pad / dg::Big16::BN), dg::Big16::THREADS,
+                                       dg::Big16::SMEM_BYTES, h->stream>>>(W, npad, Ks, out_ss);
+  else
+    dg::trmm_sumsq_kernel<dg::Big><<<(unsigned)(cols_pad / dg::Big::BN), dg::Big::THREADS,
+                                     dg::Big::SMEM_BYTES, h->stream>>>(W, npad, Ks, out_ss);
   prof_end(h, PC_TRMM_SUMSQ);
   LAUNCH_CHECK(h);
   return 0;

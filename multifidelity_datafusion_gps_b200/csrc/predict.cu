@@ -5,6 +5,7 @@
 // (never an N x M matrix in HBM beyond one chunk), the mean is reduced while it is generated, and
 // the variance comes from tmp = W Kx as a DMMA GEMM with a fused column sum-of-squares epilogue.
 #include "common.cuh"
+#include "fastmath.cuh"
 
 namespace {
 
@@ -64,6 +65,9 @@ __global__ void __launch_bounds__(256)
                            const double* __restrict__ alpha, const double* __restrict__ Xq,
                            long long ncols, long long cols_pad, double* __restrict__ Ks,
                            double* __restrict__ mean) {
+  __shared__ double stbl[64];
+  fm::load_exp_table(stbl);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (c >= cols_pad) return;
@@ -90,8 +94,8 @@ __global__ void __launch_bounds__(256)
         if (dd < d) rx = fma(t, t, rx);
         else rz = fma(t, t, rz);
       }
-      v = kp.c12 * exp(fma(kp.az, rz, kp.ax * rx));
-      if (has3) v = fma(kp.s3, exp(kp.a3 * rx), v);
+      v = kp.c12 * fm::exp_neg(fma(kp.az, rz, kp.ax * rx), stbl);
+      if (has3) v = fma(kp.s3, fm::exp_neg(kp.a3 * rx, stbl), v);
       acc = fma(v, alpha[k], acc);
     }
     if (row) row[k] = v;
@@ -200,6 +204,8 @@ __global__ void __launch_bounds__(256)
                         long long m_lo, int S, double* __restrict__ Ks, double* __restrict__ mu_c) {
   __shared__ __align__(16) double su[MC_KCHUNK], sv[MC_KCHUNK], sz[MC_KCHUNK], sa[MC_KCHUNK];
   __shared__ double macc[MC_MAXS];
+  __shared__ double stbl[64];
+  fm::load_exp_table(stbl);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long m = m_lo + blockIdx.x;
   const int d = kp.d;               // D = d + 1
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(256)
           rx = fma(t, t, rx);
         }
         su[kk] = kp.ax * rx;
-        sv[kk] = kp.s3 != 0.0 ? kp.s3 * exp(kp.a3 * rx) : 0.0;
+        sv[kk] = kp.s3 != 0.0 ? kp.s3 * fm::exp_neg(kp.a3 * rx, stbl) : 0.0;
         sz[kk] = xk[d];
         sa[kk] = alpha[k];
       } else {   // pad: exp(-inf) = 0 -> the element is exactly 0
@@ -246,8 +252,8 @@ __global__ void __launch_bounds__(256)
         const double2 a = *reinterpret_cast<const double2*>(sa + kk);
         const double t0 = z - zz.x, t1 = z - zz.y;
         double2 o;
-        o.x = fma(kp.c12, exp(fma(kp.az * t0, t0, u.x)), v.x);
-        o.y = fma(kp.c12, exp(fma(kp.az * t1, t1, u.y)), v.y);
+        o.x = fma(kp.c12, fm::exp_neg(fma(kp.az * t0, t0, u.x), stbl), v.x);
+        o.y = fma(kp.c12, fm::exp_neg(fma(kp.az * t1, t1, u.y), stbl), v.y);
         *reinterpret_cast<double2*>(row + kk) = o;
         acc = fma(o.x, a.x, acc);
         acc = fma(o.y, a.y, acc);

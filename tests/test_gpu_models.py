@@ -112,9 +112,16 @@ def test_fit_reaches_oracle_likelihood(pkg):
     ours = m.hf_model.log_likelihood()
     theirs = o.hf_model.log_likelihood()
     assert ours >= theirs - 1e-6 * abs(theirs) - 1e-3
-    # and the fitted theta evaluates to the same LML on the oracle
-    chk = go.inference(go.KIND_RBF, o.hf_model.X, o.hf_model.Y, 2, m.hf_model.param_array, want_grad=False)
-    assert abs(chk["lml"] - ours) <= 1e-6 * abs(ours) + 1e-9
+    # and the fitted theta evaluates to the same LML on the oracle.  An optimiser-chosen theta can be
+    # badly conditioned (the optimiser drives the noise towards 0: cond(K_y) ~ 1e10), where neither
+    # side can promise 1e-6: the bound is 1e-6 + a few cond(K_y) * eps ("hard
+    # parts"), and cond is part of the assertion message.
+    theta = m.hf_model.param_array
+    cond = np.linalg.cond(go.assemble_Ky(go.KIND_RBF, o.hf_model.X, 2, theta, form="direct"))
+    tol = (1e-6 + 1e-14 * cond) * abs(ours) + 1e-9
+    for form in ("direct", "gpy"):
+        chk = go.inference(go.KIND_RBF, o.hf_model.X, o.hf_model.Y, 2, theta, want_grad=False, form=form)
+        assert abs(chk["lml"] - ours) <= tol, (form, cond, chk["lml"], ours)
 
 
 def test_adaptation_with_candidate_set_improves_mse_and_matches_oracle_argmax(pkg):
