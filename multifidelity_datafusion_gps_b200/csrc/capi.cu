@@ -123,7 +123,7 @@ int mfgp_create(int device, mfgp_handle_t* out) {
             cudaMallocHost(&h->h_info, 4 * sizeof(int)) == cudaSuccess;
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
   if (ok) ok = cudaMemset(h->d_info, 0, 4 * sizeof(int)) == cudaSuccess;
-  if (!ok || linalg_configure(h) != 0) {
+  if (!ok || linalg_configure(h) != 0 || assemble_configure(h) != 0) {
     snprintf(g_err, sizeof(g_err), "mfgp_create: scratch allocation / kernel configuration failed: %s",
              cudaGetErrorString(cudaGetLastError()));
     delete h;

@@ -100,6 +100,7 @@ int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long lo
                double* out_ss);
 
 // ---- assemble.cu -------------------------------------------------------------------------
+int assemble_configure(mfgp_ctx* h);
 int assemble_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, double diag_add,
                     double* K, long long ldk, int uplo, int npad_identity);
 int grad_reduce_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, const double* Kinv,

@@ -12,7 +12,8 @@
 
 namespace fm {
 
-static __constant__ double c_exp2_tbl[64] = {
+// (plain device memory: every thread reads a different entry, which a __constant__ bank would serialise)
+static __device__ const double c_exp2_tbl[64] = {
     1, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
     1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
     1.0905077326652577, 1.1023825833078409, 1.1143867425958924, 1.1265216186082418,
@@ -30,12 +31,19 @@ static __constant__ double c_exp2_tbl[64] = {
     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.9784560263879509};
 
-// copy the table into shared memory (call from every thread of the block, then __syncthreads())
+// The lookup index differs from lane to lane, so a plain 64-entry shared table would serialise on
+// bank conflicts (ncu: the LSU was as busy as the FP64 pipe).  The table is therefore replicated 16
+// times, copy r living in bank pair r: entry j of copy r is at word j*16 + r, and a lane always reads
+// copy (lane & 15) -> the 16 lanes of a half-warp hit 16 different bank pairs whatever their j.
+constexpr int EXP_TBL_DOUBLES = 64 * 16;   // 8 KB
+
+// fill the replicated table (call from every thread of the block, then __syncthreads())
 __device__ __forceinline__ void load_exp_table(double* stbl) {
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) stbl[i] = c_exp2_tbl[i];
+  for (int i = threadIdx.x; i < EXP_TBL_DOUBLES; i += blockDim.x) stbl[i] = c_exp2_tbl[i >> 4];
 }
 
-__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ stbl) {
+// stbl_lane = stbl + (lane & 15)
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ stbl_lane) {
   const double MAGIC = 6755399441055744.0;               // 1.5 * 2^52: round-to-nearest-integer trick
   const double t = fma(x, 92.332482616893657, MAGIC);    // x * 64/ln2
   const int n = __double2loint(t);
@@ -46,7 +54,7 @@ __device__ __forceinline__ double exp_neg(double x, const double* __restrict__ s
   h = fma(h, r, 1.6666666666666666e-1);
   h = fma(h, r, 0.5);
   h = fma(h, r, 1.0);
-  const double T = stbl[n & 63];
+  const double T = stbl_lane[(n & 63) << 4];
   double res = fma(T, h * r, T);
   const int hi = __double2hiint(res) + ((n >> 6) << 20);  // scale by 2^m
   res = __hiloint2double(hi, __double2loint(res));

@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(256)
                            const double* __restrict__ alpha, const double* __restrict__ Xq,
                            long long ncols, long long cols_pad, double* __restrict__ Ks,
                            double* __restrict__ mean) {
-  __shared__ double stbl[64];
-  fm::load_exp_table(stbl);
+  __shared__ double stbl_all[fm::EXP_TBL_DOUBLES];
+  fm::load_exp_table(stbl_all);
+  const double* stbl = stbl_all + (threadIdx.x & 15);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -204,8 +205,9 @@ __global__ void __launch_bounds__(256)
                         long long m_lo, int S, double* __restrict__ Ks, double* __restrict__ mu_c) {
   __shared__ __align__(16) double su[MC_KCHUNK], sv[MC_KCHUNK], sz[MC_KCHUNK], sa[MC_KCHUNK];
   __shared__ double macc[MC_MAXS];
-  __shared__ double stbl[64];
-  fm::load_exp_table(stbl);
+  __shared__ double stbl_all[fm::EXP_TBL_DOUBLES];
+  fm::load_exp_table(stbl_all);
+  const double* stbl = stbl_all + (threadIdx.x & 15);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long m = m_lo + blockIdx.x;
   const int d = kp.d;               // D = d + 1
