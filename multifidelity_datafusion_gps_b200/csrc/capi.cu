@@ -122,6 +122,13 @@ int mfgp_create(int device, mfgp_handle_t* out) {
             cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) == cudaSuccess &&
             cudaMallocHost(&h->h_info, 4 * sizeof(int)) == cudaSuccess;
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+  for (int i = 0; ok && i < 3 * 64 + 2; i++)
+    ok = cudaEventCreateWithFlags(&h->ev_la[i], cudaEventDisableTiming) == cudaSuccess;
+  if (ok) {
+    int pr_least = 0, pr_greatest = 0;
+    ok = cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&h->s_hi, cudaStreamNonBlocking, pr_greatest) == cudaSuccess;
+  }
   if (ok) ok = cudaMemset(h->d_info, 0, 4 * sizeof(int)) == cudaSuccess;
   if (!ok || linalg_configure(h) != 0 || assemble_configure(h) != 0) {
     snprintf(g_err, sizeof(g_err), "mfgp_create: scratch allocation / kernel configuration failed: %s",
@@ -142,6 +149,8 @@ int mfgp_destroy(mfgp_handle_t h) {
   cudaFreeHost(h->h_pinned);
   cudaFreeHost(h->h_info);
   for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 3 * 64 + 2; i++) cudaEventDestroy(h->ev_la[i]);
+  if (h->s_hi) cudaStreamDestroy(h->s_hi);
   if (h->prof_ev) {
     for (int i = 0; i < MFGP_PROF_CLASSES * MFGP_PROF_POOL * 2; i++) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;

@@ -34,6 +34,10 @@ struct mfgp_ctx {
   double* h_pinned;       // 64 doubles pinned
   int* h_info;            // 4 ints pinned
   cudaEvent_t ev[8];
+  // look-ahead Cholesky: a high-priority side stream for the panel (critical-path) kernels and
+  // per-panel events ordering it against the caller's stream
+  cudaStream_t s_hi;
+  cudaEvent_t ev_la[3 * 64 + 2];
   // optional per-kernel-class timing (mfgp_profile_enable): event pairs around launches
   int prof_on;
   cudaEvent_t* prof_ev;                 // [MFGP_PROF_CLASSES][MFGP_PROF_POOL][2]

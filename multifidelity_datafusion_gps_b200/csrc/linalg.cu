@@ -318,9 +318,84 @@ int linalg_configure(mfgp_ctx* h) {
   return 0;
 }
 
+// Right-looking panels with look-ahead on top of the recursion.  Panel p (NB columns) is factorised
+// and its rows solved on the high-priority stream (the latency-bound chain of leaf kernels and narrow
+// GEMMs), which then applies panel p to the NEXT panel's block column only; the bulk of panel p's
+// trailing update runs on the caller's stream and overlaps the critical path of panel p+1.
+//   la[p]   (s_hi)  : A[next block column] -= L21 L21[next rows]^T      waits bulk[p-1] (same tiles)
+//   bulk[p] (s_main): A[beyond next block column, lower] -= L21 L21^T   waits trsm[p]
+static int LA_NB_ENV = 0;     // MFGP_LA_NB overrides the panel width (multiple of 128) for tuning
+constexpr int LA_MIN = 4096;    // below this the plain recursion is as fast
+constexpr int LA_MAXP = 64;
+// measured at N = 16384: 512 -> 55.1 ms, 768 -> 55.4, 1024 -> 56.3, 2048 -> 61.2 (profiles/r01_notes.md)
+static int la_nb(int npad) { return LA_NB_ENV ? LA_NB_ENV : (npad <= 512 * LA_MAXP ? 512 : 1024); }
+
+static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad) {
+  const long ld = npad;
+  cudaStream_t s_main = h->stream, s_hi = h->s_hi;
+  cudaEvent_t* ev_trsm = h->ev_la;
+  cudaEvent_t* ev_bulk = h->ev_la + LA_MAXP;
+  cudaEvent_t ev_start = h->ev_la[3 * LA_MAXP], ev_end = h->ev_la[3 * LA_MAXP + 1];
+  const int LA_NB = la_nb(npad);
+  int rc = 0;
+  bool bulk_pending = false;
+  CUDA_TRY(h, cudaEventRecord(ev_start, s_main));
+  CUDA_TRY(h, cudaStreamWaitEvent(s_hi, ev_start, 0));
+  const int P = (npad + LA_NB - 1) / LA_NB;
+  for (int p = 0; p < P && rc == 0; p++) {
+    const int c0 = p * LA_NB;
+    const int w = (npad - c0 < LA_NB) ? npad - c0 : LA_NB;
+    const int m = npad - c0 - w;
+    h->stream = s_hi;
+    rc = potrf_rec(h, A, W, ld, c0, w);
+    if (rc == 0 && m > 0) rc = trsm_rec(h, A, W, ld, c0 + w, m, c0, w);
+    if (rc) break;
+    if (m > 0) {
+      CUDA_TRY(h, cudaEventRecord(ev_trsm[p], s_hi));
+      const int w2 = m < LA_NB ? m : LA_NB;
+      const double* L21 = A + (long)(c0 + w) * ld + c0;
+      if (bulk_pending) CUDA_TRY(h, cudaStreamWaitEvent(s_hi, ev_bulk[p - 1], 0));
+      // look-ahead: rows c0+w.., columns [c0+w, c0+w+w2)
+      rc = launch_gemm<true, true>(h, gp(L21, ld, L21, ld, A + (long)(c0 + w) * ld + c0 + w, ld, m, w2, w,
+                                         -1.0, 1.0));
+      if (rc) break;
+      const int m2 = m - w2;
+      bulk_pending = false;
+      if (m2 > 0) {
+        h->stream = s_main;
+        CUDA_TRY(h, cudaStreamWaitEvent(s_main, ev_trsm[p], 0));
+        const double* L2 = A + (long)(c0 + w + w2) * ld + c0;
+        dg::GemmParams q = gp(L2, ld, L2, ld, A + (long)(c0 + w + w2) * ld + c0 + w + w2, ld, m2, m2, w, -1.0, 1.0);
+        q.lower_only = 1;
+        rc = launch_gemm<true, true>(h, q);
+        if (rc) break;
+        CUDA_TRY(h, cudaEventRecord(ev_bulk[p], s_main));
+        bulk_pending = true;
+      }
+    }
+  }
+  h->stream = s_main;
+  cudaEventRecord(ev_end, s_hi);
+  cudaStreamWaitEvent(s_main, ev_end, 0);
+  return rc;
+}
+
 int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad) {
   ARG_CHECK(h, npad > 0 && npad % LEAF == 0);
   CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
+  static int use_la = -1;
+  if (use_la < 0) {
+    const char* e = getenv("MFGP_LOOKAHEAD");
+    use_la = (e && atoi(e) == 0) ? 0 : 1;
+    const char* nb = getenv("MFGP_LA_NB");
+    if (nb && atoi(nb) >= 128 && atoi(nb) % 128 == 0) LA_NB_ENV = atoi(nb);
+  }
+  if (use_la && h->s_hi && npad >= LA_MIN && npad <= la_nb(npad) * LA_MAXP) {
+    cudaStream_t caller = h->stream;
+    const int rc = potrf_lookahead(h, A, W, npad);
+    h->stream = caller;   // also on the error paths inside
+    return rc;
+  }
   return potrf_rec(h, A, W, npad, 0, npad);
 }
 

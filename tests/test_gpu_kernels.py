@@ -72,6 +72,30 @@ def test_potrf_trtri_lauum_match_lapack(T, n):
     assert util.rel_err(Kinv, np.tril(np.linalg.inv(A))) < 1e-11
 
 
+@pytest.mark.parametrize("n", [4096, 5000, 6272])
+def test_potrf_lookahead_path_matches_library_cholesky(T, n):
+    # >= 4096 takes the panel/look-ahead driver (two streams); 5000 and 6272 give ragged last panels.
+    # torch.linalg.cholesky (cuSOLVER) is the checker here, never the product path.
+    torch = T.torch
+    g = torch.Generator(device="cuda").manual_seed(n)
+    B = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=g)
+    A = B @ B.T / n + torch.eye(n, dtype=torch.float64, device="cuda")
+    Ap = T.ops.pad_spd(A.clone())
+    W, info = T.ops.potrf(Ap)
+    assert info == 0
+    Lref = torch.linalg.cholesky(A)
+    L = torch.tril(Ap)[:n, :n]
+    assert ((L - Lref).abs().max() / Lref.abs().max()).item() < 1e-12
+    T.ops.trtri(Ap, W)
+    Wn = torch.tril(W)[:n, :n]
+    I = torch.eye(n, dtype=torch.float64, device="cuda")
+    assert (Wn @ L - I).abs().max().item() < 1e-10
+    # repeatability: the two-stream schedule must not change a bit
+    Ap2 = T.ops.pad_spd(A.clone())
+    T.ops.potrf(Ap2)
+    assert torch.equal(torch.tril(Ap2), torch.tril(Ap))
+
+
 def test_potrf_reports_first_bad_pivot(T):
     n = 300
     A = np.eye(n)
