@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfgp_b200.so")
+# MFGP_LIB: kernel-tuning override (tools/build_variants.sh builds A/B variants of the same library)
+LIB_PATH = os.environ.get("MFGP_LIB") or os.path.join(_HERE, "libmfgp_b200.so")
 
 KIND_RBF = 0
 KIND_COMPOSITE = 1

@@ -5,8 +5,17 @@
 // temporaries (GPy materialises three distance matrices and ~6 elementwise temporaries).
 // The product k1*k2 is folded into a single exponential, so a composite element costs two exps.
 // HBM-bound by contract (8 bytes written per element, inputs (N x D) stay in shared memory), but on
-// B200 the FP64 pipe is the tighter bound for the exponentials; fastmath.cuh's exp_neg (10 FP64
-// instructions + one table lookup) is what keeps the kernel near the memory roofline.
+// B200 the FP64 pipe is the tighter bound: 2D + 3 + 2*8 + 1 FP64 instructions per composite element
+// (30 at D = 5 -> 0.22 ms at N = 16384 with the pipe saturated, against 0.16 ms of HBM time for the
+// lower triangle; DMMA shares the FP64 units -- tools/pipe_probe.cu -- so the distances cannot be
+// moved to the tensor pipe for free).  What keeps the kernel near the memory roofline:
+//   - fastmath.cuh's exp2s (8 FP64 + 5 integer instructions + one table lookup, variances folded
+//     into the exponent),
+//   - input width D and the number of trailing z columns E as template parameters (distance loops
+//     fully unrolled, all shared-memory reads of a sub-block issued up front),
+//   - persistent CTAs (the 32 KB exp table is loaded once per CTA) that prefetch the NEXT tile's
+//     input rows with cp.async while the current tile is computed,
+//   - 2 x 4 elements per thread and sub-block, which keeps the kernel at 3 CTAs / 24 warps per SM.
 //
 // K5 replaces GPy's update_gradients_full chain (stationary.py / prod.py / add.py) for
 // dL_dK = 0.5 (alpha alpha^T - K^-1): one streaming pass over K^-1's lower triangle that
@@ -18,7 +27,25 @@
 
 namespace {
 
-constexpr int AT = 64;   // tile edge
+constexpr int BT = 128;          // CTA tile edge
+#ifndef MFGP_ASM_RI      // tuning overrides (tools/build_variants.sh); the defaults are the measured best
+#define MFGP_ASM_RI 2
+#endif
+#ifndef MFGP_ASM_CTAS
+#define MFGP_ASM_CTAS 2
+#endif
+constexpr int RI = MFGP_ASM_RI;  // rows per thread and sub-block
+// sub-block: SBR rows x SBC columns; thread (ty,tx) owns rows ty+16i and the column pairs
+// {2tx, 2tx+1} and {32+2tx, 33+2tx}: a half-warp's 16-byte accesses are then contiguous (256 B), so
+// shared-memory reads take the minimum number of wavefronts and every global store / load
+// instruction covers whole 32-byte sectors
+constexpr int SBR = 16 * RI;
+constexpr int SBC = 64;
+constexpr int NSB = (BT / SBR) * (BT / SBC);
+constexpr int CTAS_PER_SM = MFGP_ASM_CTAS;
+constexpr int MAX_DT = 8;        // widths with a specialised kernel
+
+__device__ __forceinline__ int col_of(int tx, int j) { return (j >> 1) * 32 + 2 * tx + (j & 1); }
 
 __device__ __forceinline__ void tile_from_linear(int tt, int& ti, int& tj) {
   ti = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
@@ -27,258 +54,346 @@ __device__ __forceinline__ void tile_from_linear(int tt, int& ti, int& tj) {
   tj = tt - ti * (ti + 1) / 2;
 }
 
-constexpr int BT = 128;  // CTA tile edge of the assembly / gradient kernels: 2x2 sub-blocks of AT
+__device__ __forceinline__ void cp_async8_zfill(double* sdst, const double* gsrc, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  const int n = valid ? 8 : 0;   // src-size 0: nothing is read, the destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K)); }
 
-// sX[dd][r] = X[row0 + r][dd] for r < TR (0 beyond N); dd-major so that a row of threads reads
-// consecutive shared-memory words
-template <int TR>
-__device__ __forceinline__ void load_rows(double* sX, const double* __restrict__ X, int N, int D, int row0) {
-  for (int r = threadIdx.x / 8; r < TR; r += blockDim.x / 8) {     // 8 threads per input row
-    const int gr = row0 + r;
-    for (int dd = threadIdx.x & 7; dd < D; dd += 8) sX[dd * TR + r] = gr < N ? X[(long)gr * D + dd] : 0.0;
+// sX[dd][r] = X[row0 + r][dd] for r < BT (0 beyond N), asynchronously.  The tile's rows are one
+// contiguous run of BT*D doubles of X, so the global side is perfectly coalesced; the transposition
+// to dd-major (a row of threads then reads consecutive shared-memory words) happens in the copy.
+template <int DT>
+__device__ __forceinline__ void prefetch_rows(double* sX, const double* __restrict__ X, int N, int Drt,
+                                              int row0) {
+  const int D = DT > 0 ? DT : Drt;
+  const double* base = X + (long)row0 * D;
+  for (int i = threadIdx.x; i < BT * D; i += blockDim.x) {
+    const int r = i / D, dd = i - r * D;
+    const bool ok = row0 + r < N;
+    cp_async8_zfill(sX + dd * BT + r, ok ? base + i : X, ok);
   }
 }
 
-// squared distances of the thread's 4x4 sub-block: rows ty+16i, columns 4tx+j
-template <int TR>
-__device__ __forceinline__ void sub_block_dist(const double* sXi, const double* sXj, int D, int d, int tx,
-                                               int ty, double (&rx)[4][4], double (&rz)[4][4]) {
+// Squared distances of the thread's RI x 4 sub-block.  DT > 0: width and split known at compile
+// time (x = first DT-E columns, z = the last E); DT == 0: runtime D and d.
+template <int DT, int E>
+__device__ __forceinline__ void sub_block_dist(const double* sXi, const double* sXj, int Drt, int drt,
+                                               int tx, int ty, double (&rx)[RI][4], double (&rz)[RI][4]) {
 #pragma unroll
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < RI; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) rx[i][j] = rz[i][j] = 0.0;
-  for (int dd = 0; dd < D; dd++) {
-    double xi[4], xj[4];
+  if (DT > 0) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) xi[i] = sXi[dd * TR + ty + 16 * i];          // broadcast within a half-warp
-    const double2 p0 = *reinterpret_cast<const double2*>(sXj + dd * TR + 4 * tx);   // 16-byte loads: no conflicts
-    const double2 p1 = *reinterpret_cast<const double2*>(sXj + dd * TR + 4 * tx + 2);
-    xj[0] = p0.x; xj[1] = p0.y; xj[2] = p1.x; xj[3] = p1.y;
-    if (dd < d) {
+    for (int dd = 0; dd < DT; dd++) {
+      double xi[RI], xj[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < RI; i++) xi[i] = sXi[dd * BT + ty + 16 * i];             // broadcast within a half-warp
+      const double2 p0 = *reinterpret_cast<const double2*>(sXj + dd * BT + 2 * tx);   // 16 lanes x 16 B contiguous
+      const double2 p1 = *reinterpret_cast<const double2*>(sXj + dd * BT + 32 + 2 * tx);
+      xj[0] = p0.x; xj[1] = p0.y; xj[2] = p1.x; xj[3] = p1.y;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const double t = xi[i] - xj[j];
-          rx[i][j] = fma(t, t, rx[i][j]);
-        }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < RI; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const double t = xi[i] - xj[j];
-          rz[i][j] = fma(t, t, rz[i][j]);
+          if (dd < DT - E) rx[i][j] = fma(t, t, rx[i][j]);
+          else rz[i][j] = fma(t, t, rz[i][j]);
         }
     }
-  }
-}
-
-template <bool VEC>
-__global__ void __launch_bounds__(256, 2)
-    assemble_kernel(KParams kp, const double* __restrict__ X, int N, double diag_add,
-                    double* __restrict__ K, long ldk, int lower_only, int tiles, int nrows) {
-  extern __shared__ __align__(16) double dsm[];   // sXi[D][BT] | sXj[D][BT]
-  __shared__ double stbl_all[fm::EXP_TBL_DOUBLES];
-  int ti, tj;
-  if (lower_only) {
-    tile_from_linear(blockIdx.x, ti, tj);
   } else {
-    ti = blockIdx.x / tiles;
-    tj = blockIdx.x % tiles;
-  }
-  const int D = kp.D, d = kp.d;
-  double* sXi = dsm;
-  double* sXj = dsm + D * BT;
-  fm::load_exp_table(stbl_all);
-  const double* stbl = stbl_all + (threadIdx.x & 15);
-  load_rows<BT>(sXi, X, N, D, ti * BT);
-  load_rows<BT>(sXj, X, N, D, tj * BT);
-  __syncthreads();
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const bool has3 = kp.s3 != 0.0;
-#pragma unroll 1
-  for (int sb = 0; sb < 4; sb++) {
-    const int si = sb >> 1, sj = sb & 1;
-    const int row0 = ti * BT + si * AT, col0 = tj * BT + sj * AT;
-    if (row0 >= nrows || col0 >= nrows) continue;
-    if (lower_only && col0 > row0) continue;        // sub-block strictly above the diagonal
-    double rx[4][4], rz[4][4];
-    sub_block_dist<BT>(sXi + si * AT, sXj + sj * AT, D, d, tx, ty, rx, rz);
-    if (row0 + AT <= N && col0 + AT <= N) {
-      // Interior sub-block (almost all of them): straight-line code, no per-element predicates, so
-      // the 32 exponentials of a thread are scheduled together and their constants stay in registers.
-      const double c12 = kp.c12, az = kp.az, ax = kp.ax, s3 = kp.s3, a3 = kp.a3;
-      double v[4][4];
+    for (int dd = 0; dd < Drt; dd++) {
+      double xi[RI], xj[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
+      for (int i = 0; i < RI; i++) xi[i] = sXi[dd * BT + ty + 16 * i];
+      const double2 p0 = *reinterpret_cast<const double2*>(sXj + dd * BT + 2 * tx);
+      const double2 p1 = *reinterpret_cast<const double2*>(sXj + dd * BT + 32 + 2 * tx);
+      xj[0] = p0.x; xj[1] = p0.y; xj[2] = p1.x; xj[3] = p1.y;
+      if (dd < drt) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[i][j] = c12 * fm::exp_neg(fma(az, rz[i][j], ax * rx[i][j]), stbl);
-      if (has3) {
+        for (int i = 0; i < RI; i++)
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) v[i][j] = fma(s3, fm::exp_neg(a3 * rx[i][j], stbl), v[i][j]);
-      }
-      if (row0 == col0) {
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (ty + 16 * i == 4 * tx + j) v[i][j] += diag_add;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        double* dst = K + (long)(row0 + ty + 16 * i) * ldk + col0 + 4 * tx;
-        if (VEC) {
-          reinterpret_cast<double2*>(dst)[0] = make_double2(v[i][0], v[i][1]);
-          reinterpret_cast<double2*>(dst)[1] = make_double2(v[i][2], v[i][3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; j++) dst[j] = v[i][j];
-        }
-      }
-      continue;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int r = row0 + ty + 16 * i;
-      if (r >= nrows) continue;
-      double v[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int c = col0 + 4 * tx + j;
-        double val;
-        if (r < N && c < N) {
-          val = kp.c12 * fm::exp_neg(fma(kp.az, rz[i][j], kp.ax * rx[i][j]), stbl);
-          if (has3) val = fma(kp.s3, fm::exp_neg(kp.a3 * rx[i][j], stbl), val);
-          if (r == c) val += diag_add;
-        } else {
-          val = (r == c) ? 1.0 : 0.0;   // identity pad block
-        }
-        v[j] = val;
-      }
-      double* dst = K + (long)r * ldk + col0 + 4 * tx;
-      if (VEC) {
-        // nrows is a multiple of 64 here (padded buffer): no column guard needed
-        reinterpret_cast<double2*>(dst)[0] = make_double2(v[0], v[1]);
-        reinterpret_cast<double2*>(dst)[1] = make_double2(v[2], v[3]);
+          for (int j = 0; j < 4; j++) {
+            const double t = xi[i] - xj[j];
+            rx[i][j] = fma(t, t, rx[i][j]);
+          }
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (col0 + 4 * tx + j < nrows) dst[j] = v[j];
+        for (int i = 0; i < RI; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const double t = xi[i] - xj[j];
+            rz[i][j] = fma(t, t, rz[i][j]);
+          }
       }
     }
   }
 }
 
-constexpr int GR_BLOCKS = MFGP_NUM_SMS * 4;
+// element value from the two squared distances (exp2s form, see KParams)
+template <int DT, int E>
+struct KEval {
+  double uz, ux, lc12, u3, ls3;
+  bool has3;
+  unsigned tbl;
+  __device__ __forceinline__ KEval(const KParams& kp, unsigned tbl_)
+      : uz(kp.uz), ux(kp.ux), lc12(kp.lc12), u3(kp.u3), ls3(kp.ls3), has3(kp.s3 != 0.0), tbl(tbl_) {}
+  __device__ __forceinline__ double k12(double rx, double rz) const {
+    if (DT > 0 && E == 0) return fm::exp2s(fma(ux, rx, lc12), tbl);   // no z columns: rz == 0
+    return fm::exp2s(fma(uz, rz, fma(ux, rx, lc12)), tbl);
+  }
+  __device__ __forceinline__ double k3(double rx) const { return fm::exp2s(fma(u3, rx, ls3), tbl); }
+};
 
-__global__ void __launch_bounds__(256, 2)
+template <bool VEC, int DT, int E>
+__global__ void __launch_bounds__(256, CTAS_PER_SM)
+    assemble_kernel(KParams kp, const double* __restrict__ X, int N, double diag_add,
+                    double* __restrict__ K, long ldk, int lower_only, int tiles, int nrows, int ntiles) {
+  extern __shared__ __align__(16) double dsm[];   // exp table | 2 x (sXi[D][BT] | sXj[D][BT])
+  const int D = DT > 0 ? DT : kp.D, d = DT > 0 ? DT - E : kp.d;
+  double* sX = dsm + fm::EXP_TBL_DOUBLES;
+  const int panel = 2 * D * BT;
+  fm::load_exp_table(dsm, kp.exp_tbl);
+  const KEval<DT, E> ke(kp, fm::lane_table(dsm));
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  auto tile_rc = [&](int tile, int& ti, int& tj) {
+    if (lower_only) {
+      tile_from_linear(tile, ti, tj);
+    } else {
+      ti = tile / tiles;
+      tj = tile % tiles;
+    }
+  };
+  auto prefetch = [&](int tile, int buf) {
+    int ti, tj;
+    tile_rc(tile, ti, tj);
+    prefetch_rows<DT>(sX + buf * panel, X, N, D, ti * BT);
+    prefetch_rows<DT>(sX + buf * panel + D * BT, X, N, D, tj * BT);
+  };
+  int buf = 0;
+  if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+  cp_async_commit();
+  // persistent, static round-robin over the tiles; the next tile's rows land while this one is computed
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    if (tile + (int)gridDim.x < ntiles) prefetch(tile + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    int ti, tj;
+    tile_rc(tile, ti, tj);
+    const double* sXi = sX + buf * panel;
+    const double* sXj = sXi + D * BT;
+#pragma unroll 1
+    for (int sb = 0; sb < NSB; sb++) {
+      const int si = sb >> 1, sj = sb & 1;
+      const int row0 = ti * BT + si * SBR, col0 = tj * BT + sj * SBC;
+      if (row0 >= nrows || col0 >= nrows) continue;
+      if (lower_only && col0 >= row0 + SBR) continue;   // sub-block strictly above the diagonal
+      double rx[RI][4], rz[RI][4];
+      sub_block_dist<DT, E>(sXi + si * SBR, sXj + sj * SBC, D, d, tx, ty, rx, rz);
+      if (row0 + SBR <= N && col0 + SBC <= N) {
+        // Interior sub-block (almost all of them): straight-line code, no per-element predicates
+        double v[RI][4];
+#ifdef MFGP_ASM_NOEXP     // tuning experiment: stores only
+#pragma unroll
+        for (int i = 0; i < RI; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) v[i][j] = rx[i][j] + rz[i][j];
+        if (false) {
+#else
+#pragma unroll
+        for (int i = 0; i < RI; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) v[i][j] = ke.k12(rx[i][j], rz[i][j]);
+        if (ke.has3) {
+#endif
+#pragma unroll
+          for (int i = 0; i < RI; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[i][j] += ke.k3(rx[i][j]);
+        }
+#ifdef MFGP_ASM_NOSTORE   // tuning experiment: compute only (stores predicated off by a value test)
+        {
+          double sacc = 0.0;
+#pragma unroll
+          for (int i = 0; i < RI; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) sacc += v[i][j];
+          if (sacc != 12345.678) continue;
+        }
+#endif
+        if (col0 < row0 + SBR && row0 < col0 + SBC) {   // the diagonal crosses this sub-block
+#pragma unroll
+          for (int i = 0; i < RI; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (row0 + ty + 16 * i == col0 + col_of(tx, j)) v[i][j] += diag_add;
+        }
+#pragma unroll
+        for (int i = 0; i < RI; i++) {
+          double* dst = K + (long)(row0 + ty + 16 * i) * ldk + col0 + 2 * tx;
+          if (VEC) {
+            *reinterpret_cast<double2*>(dst) = make_double2(v[i][0], v[i][1]);
+            *reinterpret_cast<double2*>(dst + 32) = make_double2(v[i][2], v[i][3]);
+          } else {
+            dst[0] = v[i][0]; dst[1] = v[i][1]; dst[32] = v[i][2]; dst[33] = v[i][3];
+          }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < RI; i++) {
+        const int r = row0 + ty + 16 * i;
+        if (r >= nrows) continue;
+        double v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int c = col0 + col_of(tx, j);
+          double val;
+          if (r < N && c < N) {
+            val = ke.k12(rx[i][j], rz[i][j]);
+            if (ke.has3) val += ke.k3(rx[i][j]);
+            if (r == c) val += diag_add;
+          } else {
+            val = (r == c) ? 1.0 : 0.0;   // identity pad block
+          }
+          v[j] = val;
+        }
+        double* dst = K + (long)r * ldk + col0;
+        if (VEC) {
+          // nrows is a multiple of 64 here (padded buffer): no column guard needed
+          *reinterpret_cast<double2*>(dst + 2 * tx) = make_double2(v[0], v[1]);
+          *reinterpret_cast<double2*>(dst + 32 + 2 * tx) = make_double2(v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (col0 + col_of(tx, j) < nrows) dst[col_of(tx, j)] = v[j];
+        }
+      }
+    }
+    __syncthreads();   // all readers done with this buffer before the next iteration refills it
+  }
+  cp_async_wait<0>();
+}
+
+constexpr int GR_BLOCKS = MFGP_NUM_SMS * CTAS_PER_SM;   // persistent; fixed tile -> block map
+
+template <int DT, int E>
+__global__ void __launch_bounds__(256, CTAS_PER_SM)
     grad_reduce_kernel(KParams kp, const double* __restrict__ X, int N,
                        const double* __restrict__ Kinv, long ld, const double* __restrict__ alpha,
                        int ntiles_lin, double* __restrict__ partials) {
-  extern __shared__ __align__(16) double dsm[];   // sXi[D][BT] | sXj[D][BT]
-  __shared__ __align__(16) double sAi_t[BT], sAj_t[BT];
+  extern __shared__ __align__(16) double dsm[];   // exp table | 2 x (sXi[D][BT] | sXj[D][BT] | ai[BT] | aj[BT])
   __shared__ double red[8][6];
-  __shared__ double stbl_all[fm::EXP_TBL_DOUBLES];
-  const int D = kp.D, d = kp.d;
-  double* sXi_t = dsm;
-  double* sXj_t = dsm + D * BT;
+  const int D = DT > 0 ? DT : kp.D, d = DT > 0 ? DT - E : kp.d;
+  double* sX = dsm + fm::EXP_TBL_DOUBLES;
+  const int panel = 2 * (D + 1) * BT;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const bool has3 = kp.s3 != 0.0;
-  fm::load_exp_table(stbl_all);
-  const double* stbl = stbl_all + (threadIdx.x & 15);
-  double S[6] = {0, 0, 0, 0, 0, 0};
-  for (int tt = blockIdx.x; tt < ntiles_lin; tt += gridDim.x) {
+  fm::load_exp_table(dsm, kp.exp_tbl);
+  const KEval<DT, E> ke(kp, fm::lane_table(dsm));
+  const bool has3 = ke.has3;
+  auto prefetch = [&](int tt, int buf) {
     int ti, tj;
     tile_from_linear(tt, ti, tj);
+    double* p = sX + buf * panel;
+    prefetch_rows<DT>(p, X, N, D, ti * BT);
+    prefetch_rows<DT>(p + D * BT, X, N, D, tj * BT);
+    const int r = (threadIdx.x < BT ? ti : tj) * BT + (threadIdx.x & (BT - 1));
+    cp_async8_zfill(p + 2 * D * BT + threadIdx.x, r < N ? alpha + r : alpha, r < N);
+  };
+  double S[6] = {0, 0, 0, 0, 0, 0};
+  int buf = 0;
+  if ((int)blockIdx.x < ntiles_lin) prefetch(blockIdx.x, 0);
+  cp_async_commit();
+  for (int tt = blockIdx.x; tt < ntiles_lin; tt += gridDim.x, buf ^= 1) {
+    if (tt + (int)gridDim.x < ntiles_lin) prefetch(tt + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
-    load_rows<BT>(sXi_t, X, N, D, ti * BT);
-    load_rows<BT>(sXj_t, X, N, D, tj * BT);
-    if (threadIdx.x < BT) {
-      int r = ti * BT + threadIdx.x;
-      sAi_t[threadIdx.x] = r < N ? alpha[r] : 0.0;
-    } else {
-      int c = tj * BT + threadIdx.x - BT;
-      sAj_t[threadIdx.x - BT] = c < N ? alpha[c] : 0.0;
-    }
-    __syncthreads();
+    int ti, tj;
+    tile_from_linear(tt, ti, tj);
+    const double* sXi_t = sX + buf * panel;
+    const double* sXj_t = sXi_t + D * BT;
+    const double* sAi_t = sXi_t + 2 * D * BT;
+    const double* sAj_t = sAi_t + BT;
 #pragma unroll 1
-   for (int sb = 0; sb < 4; sb++) {
-    const int si = sb >> 1, sj = sb & 1;
-    const int row0 = ti * BT + si * AT, col0 = tj * BT + sj * AT;
-    if (row0 >= N || col0 > row0) continue;         // beyond the data / strictly above the diagonal
-    const double* sXi = sXi_t + si * AT;
-    const double* sXj = sXj_t + sj * AT;
-    const double* sAi = sAi_t + si * AT;
-    const double* sAj = sAj_t + sj * AT;
-    // issue the K^-1 loads first so that they overlap the distance computation
-    double kin[4][4];
+    for (int sb = 0; sb < NSB; sb++) {
+      const int si = sb >> 1, sj = sb & 1;
+      const int row0 = ti * BT + si * SBR, col0 = tj * BT + sj * SBC;
+      if (row0 >= N || col0 >= row0 + SBR) continue;   // beyond the data / strictly above the diagonal
+      const double* sAi = sAi_t + si * SBR;
+      const double* sAj = sAj_t + sj * SBC;
+      // issue the K^-1 loads first so that they overlap the distance computation
+      double kin[RI][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int r = row0 + ty + 16 * i;
-      if (r < N) {
-        const double2* src = reinterpret_cast<const double2*>(Kinv + (long)r * ld + col0 + 4 * tx);
-        const double2 q0 = src[0], q1 = src[1];
-        kin[i][0] = q0.x; kin[i][1] = q0.y; kin[i][2] = q1.x; kin[i][3] = q1.y;
-      } else {
-        kin[i][0] = kin[i][1] = kin[i][2] = kin[i][3] = 0.0;
+      for (int i = 0; i < RI; i++) {
+        const int r = row0 + ty + 16 * i;
+        if (r < N) {
+          const double* src = Kinv + (long)r * ld + col0 + 2 * tx;
+          const double2 q0 = *reinterpret_cast<const double2*>(src);
+          const double2 q1 = *reinterpret_cast<const double2*>(src + 32);
+          kin[i][0] = q0.x; kin[i][1] = q0.y; kin[i][2] = q1.x; kin[i][3] = q1.y;
+        } else {
+          kin[i][0] = kin[i][1] = kin[i][2] = kin[i][3] = 0.0;
+        }
       }
-    }
-    double rx[4][4], rz[4][4];
-    sub_block_dist<BT>(sXi, sXj, D, d, tx, ty, rx, rz);
-    const double2 a0 = *reinterpret_cast<const double2*>(sAj + 4 * tx);
-    const double2 a1 = *reinterpret_cast<const double2*>(sAj + 4 * tx + 2);
-    const double aj[4] = {a0.x, a0.y, a1.x, a1.y};
-    if (col0 < row0 && row0 + AT <= N) {
-      // interior off-diagonal sub-block: every element counts twice (weight 1), no predicates
-      const double c12 = kp.c12, az = kp.az, ax = kp.ax, s3 = kp.s3, a3 = kp.a3;
+      double rx[RI][4], rz[RI][4];
+      sub_block_dist<DT, E>(sXi_t + si * SBR, sXj_t + sj * SBC, D, d, tx, ty, rx, rz);
+      const double2 a0 = *reinterpret_cast<const double2*>(sAj + 2 * tx);
+      const double2 a1 = *reinterpret_cast<const double2*>(sAj + 32 + 2 * tx);
+      const double aj[4] = {a0.x, a0.y, a1.x, a1.y};
+      if (col0 + SBC <= row0 && row0 + SBR <= N) {
+        // interior sub-block strictly below the diagonal: every element counts twice (weight 1)
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < RI; i++) {
+          const double ai = sAi[ty + 16 * i];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const double G = fma(ai, aj[j], -kin[i][j]);
+            const double gk = G * ke.k12(rx[i][j], rz[i][j]);
+            S[0] += gk;
+            if (!(DT > 0 && E == 0)) S[1] = fma(gk, rz[i][j], S[1]);
+            S[2] = fma(gk, rx[i][j], S[2]);
+            if (has3) {
+              const double g3 = G * ke.k3(rx[i][j]);
+              S[3] += g3;
+              S[4] = fma(g3, rx[i][j], S[4]);
+            }
+          }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < RI; i++) {
+        const int r = row0 + ty + 16 * i;
+        if (r >= N) continue;
         const double ai = sAi[ty + 16 * i];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const double G = ai * aj[j] - kin[i][j];
-          const double gk = G * (c12 * fm::exp_neg(fma(az, rz[i][j], ax * rx[i][j]), stbl));
+          const int c = col0 + col_of(tx, j);
+          if (c > r || c >= N) continue;
+          const double w = (c == r) ? 0.5 : 1.0;   // G = 0.5(aa^T - Kinv); off-diagonal counted twice
+          const double G = w * fma(ai, aj[j], -kin[i][j]);
+          const double gk = G * ke.k12(rx[i][j], rz[i][j]);
           S[0] += gk;
           S[1] = fma(gk, rz[i][j], S[1]);
           S[2] = fma(gk, rx[i][j], S[2]);
           if (has3) {
-            const double g3 = G * s3 * fm::exp_neg(a3 * rx[i][j], stbl);
+            const double g3 = G * ke.k3(rx[i][j]);
             S[3] += g3;
             S[4] = fma(g3, rx[i][j], S[4]);
           }
+          if (c == r) S[5] += G;
         }
       }
-      continue;
     }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const int r = row0 + ty + 16 * i;
-      if (r >= N) continue;
-      const double ai = sAi[ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int c = col0 + 4 * tx + j;
-        if (c > r || c >= N) continue;
-        const double w = (c == r) ? 0.5 : 1.0;   // G = 0.5(aa^T - Kinv); off-diagonal counted twice
-        const double G = w * (ai * aj[j] - kin[i][j]);
-        const double k12 = kp.c12 * fm::exp_neg(fma(kp.az, rz[i][j], kp.ax * rx[i][j]), stbl);
-        const double gk = G * k12;
-        S[0] += gk;
-        S[1] = fma(gk, rz[i][j], S[1]);
-        S[2] = fma(gk, rx[i][j], S[2]);
-        if (has3) {
-          const double g3 = G * kp.s3 * fm::exp_neg(kp.a3 * rx[i][j], stbl);
-          S[3] += g3;
-          S[4] = fma(g3, rx[i][j], S[4]);
-        }
-        if (c == r) S[5] += G;
-      }
-    }
-   }
+    __syncthreads();
   }
+  cp_async_wait<0>();
   // block reduction in a fixed order
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -308,13 +423,41 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
   if (lane == 0) out8[q] = v;
 }
 
+// ---- dispatch on (input width, trailing z columns) -----------------------------------------------
+// RBF kind: az == ax, so every column is treated as an x column (E = 0).  Composite: E = D - d.
+// Specialised for D <= 8 with E in {0, 1} (plain GP levels, NARGP, GPDF); everything else (GPDFC with
+// delays: composite with E > 1; D > 8) takes the runtime-width kernel.
+struct Shape {
+  int DT, E;
+};
+Shape shape_of(const KParams& kp) {
+  const int E = kp.kind == MFGP_KIND_RBF ? 0 : kp.D - kp.d;
+  if (kp.D <= MAX_DT && E <= 1) return {kp.D, E};
+  return {0, 0};
+}
+
+constexpr size_t asm_smem(int D) { return fm::EXP_TBL_BYTES + (size_t)2 * 2 * D * BT * sizeof(double); }
+constexpr size_t grad_smem(int D) { return fm::EXP_TBL_BYTES + (size_t)2 * 2 * (D + 1) * BT * sizeof(double); }
+
+#define MFGP_SHAPES(M)                                                                       \
+  M(1, 0) M(2, 0) M(3, 0) M(4, 0) M(5, 0) M(6, 0) M(7, 0) M(8, 0)                            \
+  M(2, 1) M(3, 1) M(4, 1) M(5, 1) M(6, 1) M(7, 1) M(8, 1)
+
 }  // namespace
 
 int assemble_configure(mfgp_ctx* h) {
-  const int smem = 2 * MFGP_MAX_D * BT * (int)sizeof(double);   // 64 KB at the maximum input width
-  CUDA_TRY(h, cudaFuncSetAttribute(assemble_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CUDA_TRY(h, cudaFuncSetAttribute(assemble_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  CUDA_TRY(h, cudaFuncSetAttribute(grad_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  // exp table + double-buffered row panels: 160 KB at the maximum input width (runtime-width kernels)
+  const int smem_max = (int)asm_smem(MFGP_MAX_D), gmax = (int)grad_smem(MFGP_MAX_D);
+  CUDA_TRY(h, cudaFuncSetAttribute(assemble_kernel<true, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  CUDA_TRY(h, cudaFuncSetAttribute(assemble_kernel<false, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+  CUDA_TRY(h, cudaFuncSetAttribute(grad_reduce_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, gmax));
+#define MFGP_CFG(DT, E)                                                                                   \
+  CUDA_TRY(h, cudaFuncSetAttribute(assemble_kernel<true, DT, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)asm_smem(DT)));                                                   \
+  CUDA_TRY(h, cudaFuncSetAttribute(grad_reduce_kernel<DT, E>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                   (int)grad_smem(DT)));
+  MFGP_SHAPES(MFGP_CFG)
+#undef MFGP_CFG
   return 0;
 }
 
@@ -323,14 +466,29 @@ int assemble_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, doub
   const int nrows = npad_identity > 0 ? npad_identity : N;
   const int tiles = (nrows + BT - 1) / BT;
   const int lower = uplo == MFGP_UPLO_LOWER;
-  const int grid = lower ? tiles * (tiles + 1) / 2 : tiles * tiles;
-  const bool vec = (nrows % AT == 0) && (ldk % 2 == 0) && ((uintptr_t)K % 16 == 0);
-  const size_t smem = (size_t)2 * kp.D * BT * sizeof(double);
+  const int ntiles = lower ? tiles * (tiles + 1) / 2 : tiles * tiles;
+  const int grid = ntiles < CTAS_PER_SM * MFGP_NUM_SMS ? ntiles : CTAS_PER_SM * MFGP_NUM_SMS;
+  const bool vec = (nrows % SBC == 0) && (ldk % 2 == 0) && ((uintptr_t)K % 16 == 0);
+  const Shape sh = vec ? shape_of(kp) : Shape{0, 0};
+  const size_t smem = asm_smem(kp.D);
   prof_begin(h, PC_ASSEMBLE);
-  if (vec)
-    assemble_kernel<true><<<grid, 256, smem, h->stream>>>(kp, X, N, diag_add, K, ldk, lower, tiles, nrows);
-  else
-    assemble_kernel<false><<<grid, 256, smem, h->stream>>>(kp, X, N, diag_add, K, ldk, lower, tiles, nrows);
+  bool done = false;
+#define MFGP_RUN(DT_, E_)                                                                          \
+  if (!done && sh.DT == DT_ && sh.E == E_) {                                                       \
+    assemble_kernel<true, DT_, E_><<<grid, 256, smem, h->stream>>>(kp, X, N, diag_add, K, ldk, lower, \
+                                                                   tiles, nrows, ntiles);          \
+    done = true;                                                                                   \
+  }
+  MFGP_SHAPES(MFGP_RUN)
+#undef MFGP_RUN
+  if (!done) {
+    if (vec)
+      assemble_kernel<true, 0, 0><<<grid, 256, smem, h->stream>>>(kp, X, N, diag_add, K, ldk, lower, tiles,
+                                                                  nrows, ntiles);
+    else
+      assemble_kernel<false, 0, 0><<<grid, 256, smem, h->stream>>>(kp, X, N, diag_add, K, ldk, lower, tiles,
+                                                                   nrows, ntiles);
+  }
   prof_end(h, PC_ASSEMBLE);
   LAUNCH_CHECK(h);
   return 0;
@@ -341,9 +499,19 @@ int grad_reduce_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, c
   const int tiles = (N + BT - 1) / BT;
   const int nlin = tiles * (tiles + 1) / 2;
   const int grid = nlin < GR_BLOCKS ? nlin : GR_BLOCKS;
-  const size_t smem = (size_t)2 * kp.D * BT * sizeof(double);
+  const Shape sh = shape_of(kp);
+  const size_t smem = grad_smem(kp.D);
   prof_begin(h, PC_GRAD);
-  grad_reduce_kernel<<<grid, 256, smem, h->stream>>>(kp, X, N, Kinv, ld, alpha, nlin, h->d_partials);
+  bool done = false;
+#define MFGP_RUN(DT_, E_)                                                                             \
+  if (!done && sh.DT == DT_ && sh.E == E_) {                                                          \
+    grad_reduce_kernel<DT_, E_><<<grid, 256, smem, h->stream>>>(kp, X, N, Kinv, ld, alpha, nlin,      \
+                                                               h->d_partials);                        \
+    done = true;                                                                                      \
+  }
+  MFGP_SHAPES(MFGP_RUN)
+#undef MFGP_RUN
+  if (!done) grad_reduce_kernel<0, 0><<<grid, 256, smem, h->stream>>>(kp, X, N, Kinv, ld, alpha, nlin, h->d_partials);
   prof_end(h, PC_GRAD);
   LAUNCH_CHECK(h);
   reduce_partials_kernel<<<1, 192, 0, h->stream>>>(h->d_partials, grid, d_out8);

@@ -25,6 +25,7 @@ int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, 
                         long long m_global0, long long m_lo, long long npts, int S,
                         long long cols_pad, double* Ks, double* mu_c);
 int mc_max_samples();
+int predict_configure(mfgp_ctx* h);
 int sqrt_launch(mfgp_ctx* h, double* v, long long n);
 int mc_aggregate_launch(mfgp_ctx* h, const double* mu_c, const double* v_c, long long npts, int S,
                         double* mean, double* var);
@@ -70,6 +71,22 @@ int make_kparams(mfgp_ctx* h, int kind, int D, int d, const double* theta, int P
     ARG_CHECK(h, kind == MFGP_KIND_RBF || kind == MFGP_KIND_COMPOSITE);
   }
   ARG_CHECK(h, theta[P - 1] >= 0.0);
+  {  // exp2s() form (fastmath.cuh): coefficients in units of ln2/256, variances as additive logs
+    const double U = 369.32993046757463;   // 256 / ln 2
+    // The optimiser's line search visits absurd variances (softplus of a large negative number);
+    // outside e^+-700 the log-variance is clamped: below, the term is < 1e-304 either way; above,
+    // FP64 would overflow in GPy's form as well.
+    double l12 = kind == MFGP_KIND_COMPOSITE ? log(theta[0]) + log(theta[2]) : log(theta[0]);
+    double l3 = kp->s3 > 0.0 ? log(kp->s3) : 0.0;
+    l12 = fmin(fmax(l12, -700.0), 700.0);
+    l3 = fmin(fmax(l3, -700.0), 700.0);
+    kp->uz = kp->az * U;
+    kp->ux = kp->ax * U;
+    kp->u3 = kp->a3 * U;
+    kp->lc12 = l12 * U;
+    kp->ls3 = l3 * U;
+    kp->exp_tbl = h->d_exp_tbl;
+  }
   kp->noise = theta[P - 1];
   for (int i = 0; i < P; i++) kp->theta[i] = theta[i];
   return 0;
@@ -119,6 +136,8 @@ int mfgp_create(int device, mfgp_handle_t* out) {
   bool ok = cudaMalloc(&h->d_partials, MFGP_PARTIALS * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_scalars, MFGP_SMALL * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_info, 4 * sizeof(int)) == cudaSuccess &&
+            cudaMalloc(&h->d_exp_tbl, 256 * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&h->d_counters, 16 * sizeof(int)) == cudaSuccess &&
             cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) == cudaSuccess &&
             cudaMallocHost(&h->h_info, 4 * sizeof(int)) == cudaSuccess;
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
@@ -129,8 +148,14 @@ int mfgp_create(int device, mfgp_handle_t* out) {
     ok = cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest) == cudaSuccess &&
          cudaStreamCreateWithPriority(&h->s_hi, cudaStreamNonBlocking, pr_greatest) == cudaSuccess;
   }
-  if (ok) ok = cudaMemset(h->d_info, 0, 4 * sizeof(int)) == cudaSuccess;
-  if (!ok || linalg_configure(h) != 0 || assemble_configure(h) != 0) {
+  if (ok) ok = cudaMemset(h->d_info, 0, 4 * sizeof(int)) == cudaSuccess &&
+               cudaMemset(h->d_counters, 0, 16 * sizeof(int)) == cudaSuccess;
+  if (ok) {   // 2^(j/256) rounded from 64-bit-mantissa long double
+    double tbl[256];
+    for (int j = 0; j < 256; j++) tbl[j] = (double)exp2l((long double)j / 256.0L);
+    ok = cudaMemcpy(h->d_exp_tbl, tbl, sizeof(tbl), cudaMemcpyHostToDevice) == cudaSuccess;
+  }
+  if (!ok || linalg_configure(h) != 0 || assemble_configure(h) != 0 || predict_configure(h) != 0) {
     snprintf(g_err, sizeof(g_err), "mfgp_create: scratch allocation / kernel configuration failed: %s",
              cudaGetErrorString(cudaGetLastError()));
     delete h;
@@ -146,6 +171,8 @@ int mfgp_destroy(mfgp_handle_t h) {
   cudaFree(h->d_partials);
   cudaFree(h->d_scalars);
   cudaFree(h->d_info);
+  cudaFree(h->d_exp_tbl);
+  cudaFree(h->d_counters);
   cudaFreeHost(h->h_pinned);
   cudaFreeHost(h->h_info);
   for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);

@@ -14,12 +14,18 @@
 //   K(a,b) = c12 * exp(az * |z_a-z_b|^2 + ax * |x_a-x_b|^2) + s3 * exp(a3 * |x_a-x_b|^2)
 // COMPOSITE: c12 = var1*var2, az = -1/(2 len1^2), ax = -1/(2 len2^2), s3 = var3, a3 = -1/(2 len3^2)
 // RBF      : c12 = var, az = ax = -1/(2 len^2), s3 = 0   (x = first d columns, z = the rest)
+// The device kernels evaluate both exponentials with fastmath.cuh's exp2s(), whose argument is in
+// units of ln2/256 and carries the variance as an additive constant:
+//   K(a,b) = exp2s(uz*|dz|^2 + ux*|dx|^2 + lc12) + exp2s(u3*|dx|^2 + ls3)      (second term iff s3 != 0)
+//   uz = az*256/ln2, ux = ax*256/ln2, u3 = a3*256/ln2, lc12 = log(c12)*256/ln2, ls3 = log(s3)*256/ln2
 struct KParams {
   int kind, d, D;
   double c12, az, ax, s3, a3;
+  double uz, ux, u3, lc12, ls3;
   double kdiag;   // K(a,a)
   double noise;   // Gaussian_noise.variance
   double theta[8];
+  const double* exp_tbl;   // device, 256 doubles: 2^(j/256) (mfgp_ctx::d_exp_tbl)
 };
 
 struct mfgp_ctx {
@@ -31,6 +37,8 @@ struct mfgp_ctx {
   double* d_partials;     // MFGP_PARTIALS doubles: per-block partial sums
   double* d_scalars;      // 64 doubles: results staged for the host
   int* d_info;            // 4 ints: [0] first bad pivot (1-based, 0 = ok)
+  double* d_exp_tbl;      // 256 doubles: 2^(j/256), correctly rounded on the host
+  int* d_counters;        // 16 ints: dynamic tile counters (zeroed before use)
   double* h_pinned;       // 64 doubles pinned
   int* h_info;            // 4 ints pinned
   cudaEvent_t ev[8];

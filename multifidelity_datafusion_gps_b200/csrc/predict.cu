@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(256)
                            long long ncols, long long cols_pad, double* __restrict__ Ks,
                            double* __restrict__ mean) {
   __shared__ double stbl_all[fm::EXP_TBL_DOUBLES];
-  fm::load_exp_table(stbl_all);
-  const double* stbl = stbl_all + (threadIdx.x & 15);
+  fm::load_exp_table(stbl_all, kp.exp_tbl);
+  const unsigned tbl = fm::lane_table(stbl_all);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(256)
         if (dd < d) rx = fma(t, t, rx);
         else rz = fma(t, t, rz);
       }
-      v = kp.c12 * fm::exp_neg(fma(kp.az, rz, kp.ax * rx), stbl);
-      if (has3) v = fma(kp.s3, fm::exp_neg(kp.a3 * rx, stbl), v);
+      v = fm::exp2s(fma(kp.uz, rz, fma(kp.ux, rx, kp.lc12)), tbl);
+      if (has3) v += fm::exp2s(fma(kp.u3, rx, kp.ls3), tbl);
       acc = fma(v, alpha[k], acc);
     }
     if (row) row[k] = v;
@@ -190,9 +190,9 @@ __global__ void build_mc_rows_kernel(const double* __restrict__ Xtest, const dou
 
 // K7 generator: one CTA per test point m, all S samples of it.  Only k1(z_s, Z_k) depends on the
 // sample, so the x-dependent factors are computed once per (m, k) into shared memory
-//   su[k] = ax |x_m - X_k|^2,  sv[k] = s3 exp(a3 |x_m - X_k|^2),  sz[k] = Z_k,  sa[k] = alpha_k
-// and every (sample, k) element then costs ONE exponential:
-//   Ks[(m,s)][k] = c12 exp(az (z_s - Z_k)^2 + su[k]) + sv[k],   mu[(m,s)] = sum_k Ks alpha_k.
+//   su[k] = ux |x_m - X_k|^2 + lc12,  sv[k] = exp2s(u3 |x_m - X_k|^2 + ls3),  sz[k] = Z_k,  sa[k] = alpha_k
+// (exp2s units, see KParams) and every (sample, k) element then costs ONE exponential:
+//   Ks[(m,s)][k] = exp2s(uz (z_s - Z_k)^2 + su[k]) + sv[k],   mu[(m,s)] = sum_k Ks alpha_k.
 // Columns are written with 16-byte stores; the per-sample mean is reduced in a fixed order.
 constexpr int MC_KCHUNK = 1024;   // k values staged per pass (4 arrays x 8 KB, static smem)
 constexpr int MC_MAXS = 1024;
@@ -203,17 +203,18 @@ __global__ void __launch_bounds__(256)
                         const double* __restrict__ mu_l, const double* __restrict__ sd_l,
                         const double* __restrict__ eps, unsigned long long seed, long long m_global0,
                         long long m_lo, int S, double* __restrict__ Ks, double* __restrict__ mu_c) {
+  extern __shared__ __align__(16) double stbl_all[];   // exp table (dynamic: 32 KB)
   __shared__ __align__(16) double su[MC_KCHUNK], sv[MC_KCHUNK], sz[MC_KCHUNK], sa[MC_KCHUNK];
   __shared__ double macc[MC_MAXS];
-  __shared__ double stbl_all[fm::EXP_TBL_DOUBLES];
-  fm::load_exp_table(stbl_all);
-  const double* stbl = stbl_all + (threadIdx.x & 15);
+  fm::load_exp_table(stbl_all, kp.exp_tbl);
+  const unsigned tbl = fm::lane_table(stbl_all);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long m = m_lo + blockIdx.x;
   const int d = kp.d;               // D = d + 1
   double xm[MFGP_MAX_D];
   for (int dd = 0; dd < d; dd++) xm[dd] = Xtest[m * d + dd];
   const double mul = mu_l[m], sdl = sd_l[m];
+  const double uz = kp.uz;
   for (int s = tid; s < S; s += 256) macc[s] = 0.0;
   for (int k0 = 0; k0 < npad; k0 += MC_KCHUNK) {
     const int klen = min(MC_KCHUNK, npad - k0);
@@ -227,12 +228,12 @@ __global__ void __launch_bounds__(256)
           const double t = xm[dd] - xk[dd];
           rx = fma(t, t, rx);
         }
-        su[kk] = kp.ax * rx;
-        sv[kk] = kp.s3 != 0.0 ? kp.s3 * fm::exp_neg(kp.a3 * rx, stbl) : 0.0;
+        su[kk] = fma(kp.ux, rx, kp.lc12);
+        sv[kk] = kp.s3 != 0.0 ? fm::exp2s(fma(kp.u3, rx, kp.ls3), tbl) : 0.0;
         sz[kk] = xk[d];
         sa[kk] = alpha[k];
-      } else {   // pad: exp(-inf) = 0 -> the element is exactly 0
-        su[kk] = -INFINITY;
+      } else {   // pad: the element is forced to exactly 0 below
+        su[kk] = 0.0;
         sv[kk] = 0.0;
         sz[kk] = 0.0;
         sa[kk] = 0.0;
@@ -247,18 +248,30 @@ __global__ void __launch_bounds__(256)
       const double z = fma(sdl, e, mul);
       double* row = Ks + ((long long)blockIdx.x * S + s) * npad + k0;
       double acc = 0.0;
-      for (int kk = 2 * lane; kk < klen; kk += 64) {
+      const int kval = min(klen, N - k0);        // training points in this chunk (the rest is pad)
+      const int kfull = kval & ~1;
+      for (int kk = 2 * lane; kk < kfull; kk += 64) {
         const double2 u = *reinterpret_cast<const double2*>(su + kk);
         const double2 v = *reinterpret_cast<const double2*>(sv + kk);
         const double2 zz = *reinterpret_cast<const double2*>(sz + kk);
         const double2 a = *reinterpret_cast<const double2*>(sa + kk);
         const double t0 = z - zz.x, t1 = z - zz.y;
         double2 o;
-        o.x = fma(kp.c12, fm::exp_neg(fma(kp.az * t0, t0, u.x), stbl), v.x);
-        o.y = fma(kp.c12, fm::exp_neg(fma(kp.az * t1, t1, u.y), stbl), v.y);
+        o.x = fm::exp2s(fma(uz * t0, t0, u.x), tbl) + v.x;
+        o.y = fm::exp2s(fma(uz * t1, t1, u.y), tbl) + v.y;
         *reinterpret_cast<double2*>(row + kk) = o;
         acc = fma(o.x, a.x, acc);
         acc = fma(o.y, a.y, acc);
+      }
+      // ragged end: at most one training point, then the zero pad up to the 128-multiple
+      for (int kk = kfull + 2 * lane; kk < klen; kk += 64) {
+        double2 o = make_double2(0.0, 0.0);
+        if (kk < kval) {
+          const double t0 = z - sz[kk];
+          o.x = fm::exp2s(fma(uz * t0, t0, su[kk]), tbl) + sv[kk];
+          acc = fma(o.x, sa[kk], acc);
+        }
+        *reinterpret_cast<double2*>(row + kk) = o;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -524,8 +537,8 @@ int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, 
   if (npts <= 0) return 0;
   ARG_CHECK(h, S <= MC_MAXS);
   prof_begin(h, PC_CROSSGEN);
-  cross_gen_mc_kernel<<<(unsigned)npts, 256, 0, h->stream>>>(kp, X, N, npad, alpha, Xtest, mu_l, sd_l,
-                                                             eps, seed, m_global0, m_lo, S, Ks, mu_c);
+  cross_gen_mc_kernel<<<(unsigned)npts, 256, fm::EXP_TBL_BYTES, h->stream>>>(
+      kp, X, N, npad, alpha, Xtest, mu_l, sd_l, eps, seed, m_global0, m_lo, S, Ks, mu_c);
   prof_end(h, PC_CROSSGEN);
   LAUNCH_CHECK(h);
   const long long tail = (cols_pad - npts * S) * npad;
@@ -537,6 +550,12 @@ int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, 
 }
 
 int mc_max_samples() { return MC_MAXS; }
+
+int predict_configure(mfgp_ctx* h) {
+  CUDA_TRY(h, cudaFuncSetAttribute(cross_gen_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   fm::EXP_TBL_BYTES));
+  return 0;
+}
 
 int finish_var_launch(mfgp_ctx* h, const double* ss, long long n, double kdiag, double noise_add,
                       double* var) {
