@@ -7,15 +7,22 @@
 // HBM-bound by contract (8 bytes written per element, inputs (N x D) stay in shared memory), but on
 // B200 the FP64 pipe is the tighter bound: 2D + 3 + 2*8 + 1 FP64 instructions per composite element
 // (30 at D = 5 -> 0.22 ms at N = 16384 with the pipe saturated, against 0.16 ms of HBM time for the
-// lower triangle; DMMA shares the FP64 units -- tools/pipe_probe.cu -- so the distances cannot be
-// moved to the tensor pipe for free).  What keeps the kernel near the memory roofline:
+// lower triangle).  DMMA is no way out: it shares the FP64 units (tools/pipe_probe.cu: DFMA and DMMA
+// streams serialise) and has the same FMA rate, so distances as a k-padded DMMA product cost as much
+// as the direct form (tried in r01: 0.40 ms, tensor 31 % + fp64 34 %).  What keeps the kernel close:
 //   - fastmath.cuh's exp2s (8 FP64 + 5 integer instructions + one table lookup, variances folded
 //     into the exponent),
 //   - input width D and the number of trailing z columns E as template parameters (distance loops
 //     fully unrolled, all shared-memory reads of a sub-block issued up front),
 //   - persistent CTAs (the 32 KB exp table is loaded once per CTA) that prefetch the NEXT tile's
 //     input rows with cp.async while the current tile is computed,
-//   - 2 x 4 elements per thread and sub-block, which keeps the kernel at 3 CTAs / 24 warps per SM.
+//   - a thread mapping whose 16-byte shared reads and global stores are contiguous per half-warp
+//     (minimum LDS wavefronts; every STG covers whole 32-byte sectors: the store pattern alone
+//     sustains 5.3 TB/s),
+//   - 2 x 4 elements per thread and sub-block at 2 CTAs per SM (119 registers, the eight exponentials
+//     of a thread interleaved by the scheduler).
+// Measured (tools/exp_probe.cu): exp2s sustains 25 cycles per warp against the 16-cycle FP64 bound --
+// the table LDS.64 costs ~4 cycles of issue, the clamp ~2 -- which is what holds K1 at ~0.36 ms.
 //
 // K5 replaces GPy's update_gradients_full chain (stationary.py / prod.py / add.py) for
 // dL_dK = 0.5 (alpha alpha^T - K^-1): one streaming pass over K^-1's lower triangle that
@@ -195,43 +202,19 @@ __global__ void __launch_bounds__(256, CTAS_PER_SM)
       if (lower_only && col0 >= row0 + SBR) continue;   // sub-block strictly above the diagonal
       double rx[RI][4], rz[RI][4];
       sub_block_dist<DT, E>(sXi + si * SBR, sXj + sj * SBC, D, d, tx, ty, rx, rz);
-      if (row0 + SBR <= N && col0 + SBC <= N) {
+      const bool on_diag = col0 < row0 + SBR && row0 < col0 + SBC;   // the diagonal crosses this sub-block
+      if (row0 + SBR <= N && col0 + SBC <= N && !on_diag) {
         // Interior sub-block (almost all of them): straight-line code, no per-element predicates
         double v[RI][4];
-#ifdef MFGP_ASM_NOEXP     // tuning experiment: stores only
-#pragma unroll
-        for (int i = 0; i < RI; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) v[i][j] = rx[i][j] + rz[i][j];
-        if (false) {
-#else
 #pragma unroll
         for (int i = 0; i < RI; i++)
 #pragma unroll
           for (int j = 0; j < 4; j++) v[i][j] = ke.k12(rx[i][j], rz[i][j]);
         if (ke.has3) {
-#endif
 #pragma unroll
           for (int i = 0; i < RI; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) v[i][j] += ke.k3(rx[i][j]);
-        }
-#ifdef MFGP_ASM_NOSTORE   // tuning experiment: compute only (stores predicated off by a value test)
-        {
-          double sacc = 0.0;
-#pragma unroll
-          for (int i = 0; i < RI; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) sacc += v[i][j];
-          if (sacc != 12345.678) continue;
-        }
-#endif
-        if (col0 < row0 + SBR && row0 < col0 + SBC) {   // the diagonal crosses this sub-block
-#pragma unroll
-          for (int i = 0; i < RI; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (row0 + ty + 16 * i == col0 + col_of(tx, j)) v[i][j] += diag_add;
         }
 #pragma unroll
         for (int i = 0; i < RI; i++) {
@@ -279,6 +262,7 @@ __global__ void __launch_bounds__(256, CTAS_PER_SM)
   }
   cp_async_wait<0>();
 }
+
 
 constexpr int GR_BLOCKS = MFGP_NUM_SMS * CTAS_PER_SM;   // persistent; fixed tile -> block map
 
