@@ -135,12 +135,27 @@ int mfgp_augment(mfgp_handle_t h, const mfgp_level_t* lf, const double* d_X, lon
  * (mu_s, v_s) = HF predict at [x, z]; mean = mean_s mu_s; var = mean_s v_s + var_s(mu_s).
  * d_eps: (M, S) standard normals, or NULL -> Philox4x32-10 keyed by seed, counter = (m0+m)*S+s.
  * d_weights: optional (M,) quadrature weights; h_wsum[0] += sum_m w_m mean_m (PCE mean).
- * Only E = 1 (NARGP: offsets = {0}) is supported by this entry point. */
+ * E = 1 (NARGP: offsets = {0}) only; mfgp_predict_mc_delays handles E > 1. */
 int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
                     const double* d_Xtest, long long M, int S, const double* d_eps,
                     unsigned long long seed, long long m0, int include_lf_noise,
                     int include_hf_noise, const double* d_weights, double* d_mean, double* d_var,
                     double* h_wsum, double* d_ws, size_t ws_bytes);
+
+/* K7 for models with delays (GPDF / GPDFC: E = n*d + 1 augmented columns, 1 <= E <= 8).  The
+ * low-fidelity posterior at the E locations x + o_e tau of a test point is JOINT: mu_l in R^E,
+ * Sigma_l = k(a,a') - (W k_a).(W k_a') in R^(E x E) (+ (noise + lf_jitter) I), z_s = mu_l + chol(Sigma_l) eps_s,
+ * then (mu_s, v_s) = HF predict at [x, z_s] and the same aggregation as mfgp_predict_mc.
+ * h_offsets: HOST (E, d) iterator offsets (src/augm_iterators/backward_augm_iterator.py:20-37).
+ * d_eps: (M, S, E) standard normals, or NULL -> Philox counter ((m0+m)*S + s)*E + e.
+ * Returns >0: 1-based global index of the first test point whose Sigma_l is not positive definite
+ * (raise lf_jitter, as np.linalg.cholesky would raise LinAlgError in the NumPy restatement). */
+int mfgp_predict_mc_delays(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
+                           const double* d_Xtest, long long M, const double* h_offsets, int E,
+                           double tau, int S, const double* d_eps, unsigned long long seed,
+                           long long m0, int include_lf_noise, int include_hf_noise, double lf_jitter,
+                           const double* d_weights, double* d_mean, double* d_var, double* h_wsum,
+                           double* d_ws, size_t ws_bytes);
 
 /* the eps the in-kernel generator uses, for the parity tests: out[i] = N(0,1) of counter first+i */
 int mfgp_fill_normal(mfgp_handle_t h, unsigned long long seed, long long first, long long count,

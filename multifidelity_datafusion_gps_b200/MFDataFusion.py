@@ -160,45 +160,71 @@ class MultifidelityDataFusion(AbstractMFGP):
 
     # -- A8 Monte-Carlo propagation (extension) ------------------------------------------------------
     def predict_mc_device(self, dX, n_samples=100, d_eps=None, seed=0, m0=0, d_weights=None,
-                          include_lf_noise=True, ws_bytes=None):
-        """dX (M,d) CUDA -> (mean (M,), var (M,), weighted sum or None).  d_eps: optional (M, S) CUDA
-        standard normals; otherwise Philox keyed by (seed, global point index m0+m, sample)."""
+                          include_lf_noise=True, ws_bytes=None, lf_jitter=0.0):
+        """dX (M,d) CUDA -> (mean (M,), var (M,), weighted sum or None).  d_eps: optional CUDA standard
+        normals, (M, S) for E = 1 and (M, S, E) for models with delays; otherwise Philox keyed by
+        (seed, global point index m0+m, sample, column).  E = 1 (NARGP) samples the LF marginal;
+        E > 1 (GPDF / GPDFC) samples the JOINT LF posterior at the E augmented locations."""
         assert self.data_driven_lf_approach, "MC propagation needs a data-driven low-fidelity GP"
-        assert self.augm_iterator.new_entries_count() == 1, "predict_mc supports E = 1 (NARGP)"
+        E = self.augm_iterator.new_entries_count()
         h = _ffi.get_handle(self.device)
         self._apply_add_noise()
         lf, hf = self.lf_model.level_struct(), self.hf_model.level_struct()
         M, S = int(dX.shape[0]), int(n_samples)
         mean = torch.empty(M, dtype=torch.float64, device=dX.device)
         var = torch.empty(M, dtype=torch.float64, device=dX.device)
-        if ws_bytes is None:
-            per_col = (self.hf_model.npad + self.input_dim + 3) * 8
-            want = 16 * M + 148 * 128 * 4 * per_col
-            need = 16 * M + max((S + 256) * per_col, (self.lf_model.npad + 1) * 128 * 8) + 4096
-            ws_bytes = max(min(want, 2 << 30), need)
-        ws = gp.workspace(self.device, ws_bytes)
         wsum = ctypes.c_double(0.0) if d_weights is not None else None
-        h.check(h.lib.mfgp_predict_mc(
-            h.h, ctypes.byref(lf), ctypes.byref(hf), dX.data_ptr(), M, S,
+        npl, nph, d = self.lf_model.npad, self.hf_model.npad, self.input_dim
+        if E == 1:
+            if ws_bytes is None:
+                per_col = (nph + d + 3) * 8
+                want = 16 * M + 148 * 128 * 4 * per_col
+                need = 16 * M + max((S + 256) * per_col, (npl + 1) * 128 * 8) + 4096
+                ws_bytes = max(min(want, 2 << 30), need)
+            ws = gp.workspace(self.device, ws_bytes)
+            h.check(h.lib.mfgp_predict_mc(
+                h.h, ctypes.byref(lf), ctypes.byref(hf), dX.data_ptr(), M, S,
+                d_eps.data_ptr() if d_eps is not None else None, int(seed), int(m0),
+                int(include_lf_noise), 1, d_weights.data_ptr() if d_weights is not None else None,
+                mean.data_ptr(), var.data_ptr(), ctypes.byref(wsum) if wsum is not None else None,
+                ws.data_ptr(), ws.numel() * 8))
+            return mean, var, (wsum.value if wsum is not None else None)
+        assert E <= 8, "joint low-fidelity sampling supports at most 8 augmented columns"
+        offs = np.ascontiguousarray(self.augm_iterator.offset_table(), dtype=np.float64)
+        if ws_bytes is None:
+            per_pt = E + E * E + max(E * (d + 2 * npl + 1) + E * (E + 1) // 2, S * (d + E + nph + 2))
+            slack = 256 * (2 * npl + nph + d + E + 4)
+            want = 8 * (slack + per_pt * min(M, max(1, 148 * 128 * 4 // S)))
+            ws_bytes = max(min(want, 2 << 30), 8 * (slack + per_pt))
+        ws = gp.workspace(self.device, ws_bytes)
+        rc = h.lib.mfgp_predict_mc_delays(
+            h.h, ctypes.byref(lf), ctypes.byref(hf), dX.data_ptr(), M,
+            offs.ctypes.data_as(ctypes.c_void_p), E, float(self.tau), S,
             d_eps.data_ptr() if d_eps is not None else None, int(seed), int(m0),
-            int(include_lf_noise), 1, d_weights.data_ptr() if d_weights is not None else None,
-            mean.data_ptr(), var.data_ptr(), ctypes.byref(wsum) if wsum is not None else None,
-            ws.data_ptr(), ws.numel() * 8))
+            int(include_lf_noise), 1, float(lf_jitter),
+            d_weights.data_ptr() if d_weights is not None else None, mean.data_ptr(), var.data_ptr(),
+            ctypes.byref(wsum) if wsum is not None else None, ws.data_ptr(), ws.numel() * 8)
+        if rc > 0:
+            raise np.linalg.LinAlgError(
+                "joint low-fidelity covariance of test point %d is not positive definite; pass lf_jitter" % (rc - 1))
+        h.check(rc)
         return mean, var, (wsum.value if wsum is not None else None)
 
     def predict_mc(self, X_test, n_samples=100, eps=None, seed=0, weights=None, include_lf_noise=True,
-                   m0=0):
-        """NumPy front end of predict_mc_device.  eps: optional (M, S) or (M, S, 1) standard normals.
-        m0: global index of the first test point (keys the in-kernel generator when eps is None).
+                   m0=0, lf_jitter=0.0):
+        """NumPy front end of predict_mc_device.  eps: optional standard normals, (M, S[, 1]) for E = 1,
+        (M, S, E) for models with delays.  m0: global index of the first test point (keys the in-kernel
+        generator when eps is None).  lf_jitter: added to the diagonal of the joint LF covariance (E > 1).
         Returns (mean (M,1), var (M,1)); with `weights` also sets ``self.last_pce_mean``."""
         assert X_test.ndim == 2 and X_test.shape[1] == self.input_dim
+        E = self.augm_iterator.new_entries_count()
         d_eps = None
         if eps is not None:
-            eps = np.asarray(eps, dtype=np.float64).reshape(X_test.shape[0], n_samples)
+            eps = np.asarray(eps, dtype=np.float64).reshape(X_test.shape[0], n_samples, E)
             d_eps = gp.to_device(eps, self.device)
         d_w = gp.to_device(np.asarray(weights).ravel(), self.device) if weights is not None else None
         mean, var, wsum = self.predict_mc_device(gp.to_device(X_test, self.device), n_samples, d_eps,
-                                                 seed, m0, d_w, include_lf_noise)
+                                                 seed, m0, d_w, include_lf_noise, lf_jitter=lf_jitter)
         self.last_pce_mean = wsum
         return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]
 

@@ -21,7 +21,8 @@ EXPORTS = [
     "mfgp_version", "mfgp_padded_n", "mfgp_create", "mfgp_destroy", "mfgp_set_stream",
     "mfgp_last_error", "mfgp_launch_count", "mfgp_profile_enable", "mfgp_profile_read", "mfgp_assemble", "mfgp_factorize", "mfgp_lml_grad",
     "mfgp_lml_grad_timed", "mfgp_potrf", "mfgp_trtri", "mfgp_lauum", "mfgp_predict_ws_bytes",
-    "mfgp_predict", "mfgp_augment", "mfgp_predict_mc", "mfgp_fill_normal", "mfgp_argmax",
+    "mfgp_predict", "mfgp_augment", "mfgp_predict_mc", "mfgp_predict_mc_delays", "mfgp_fill_normal",
+    "mfgp_argmax",
 ]
 
 
@@ -84,6 +85,9 @@ def load_library():
     lib.mfgp_augment.argtypes = [vp, ctypes.POINTER(Level), vp, c_ll, vp, c_int, c_dbl, vp, vp, c_sz]
     lib.mfgp_predict_mc.argtypes = [vp, ctypes.POINTER(Level), ctypes.POINTER(Level), vp, c_ll, c_int,
                                     vp, c_ull, c_ll, c_int, c_int, vp, vp, vp, vp, vp, c_sz]
+    lib.mfgp_predict_mc_delays.argtypes = [vp, ctypes.POINTER(Level), ctypes.POINTER(Level), vp, c_ll, vp, c_int,
+                                           c_dbl, c_int, vp, c_ull, c_ll, c_int, c_int, c_dbl, vp, vp, vp, vp,
+                                           vp, c_sz]
     lib.mfgp_fill_normal.argtypes = [vp, c_ull, c_ll, c_ll, vp]
     lib.mfgp_argmax.argtypes = [vp, vp, c_ll, vp, vp]
     for name in EXPORTS:

@@ -30,6 +30,12 @@ int sqrt_launch(mfgp_ctx* h, double* v, long long n);
 int mc_aggregate_launch(mfgp_ctx* h, const double* mu_c, const double* v_c, long long npts, int S,
                         double* mean, double* var);
 int argmax_launch(mfgp_ctx* h, const double* v, long long n, double* d_val, long long* d_idx);
+int group_gram_launch(mfgp_ctx* h, const double* T, int npad, long long ldt, long long npts, int E, double* G);
+int joint_chol_launch(mfgp_ctx* h, const double* G, const double* d_kab, long long npts, int E,
+                      double diag_add, long long p_global0, double* Lc);
+int build_mc_rows_joint_launch(mfgp_ctx* h, const double* Xtest, const double* mu_l, const double* Lc,
+                               const double* eps, unsigned long long seed, long long m_global0,
+                               long long m_lo, long long ncols, int S, int d, int E, double* out);
 int wdot_launch(mfgp_ctx* h, const double* w, const double* x, long long n, double* d_out);
 
 #define JITTER_CONST 1e-8   // GPy exact_gaussian_inference.py: diag.add(Ky, variance + 1e-8)
@@ -503,6 +509,98 @@ int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t*
     h_wsum[0] += h->h_pinned[20];
   }
   return 0;
+}
+
+int mfgp_predict_mc_delays(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
+                           const double* d_Xtest, long long M, const double* h_offsets, int E,
+                           double tau, int S, const double* d_eps, unsigned long long seed,
+                           long long m0, int include_lf_noise, int include_hf_noise, double lf_jitter,
+                           const double* d_weights, double* d_mean, double* d_var, double* h_wsum,
+                           double* d_ws, size_t ws_bytes) {
+  ENTER(h);
+  KParams kl, kh;
+  int rc;
+  if ((rc = level_kparams(h, lf, &kl))) return rc;
+  if ((rc = level_kparams(h, hf, &kh))) return rc;
+  const int d = lf->D;
+  ARG_CHECK(h, lf->kind == MFGP_KIND_RBF);              // the reference's low-fidelity GP: RBF(d)
+  ARG_CHECK(h, h_offsets && E >= 1 && E <= 8 && hf->D == d + E && (hf->d == d || hf->kind == MFGP_KIND_RBF));
+  ARG_CHECK(h, lf->d_W && hf->d_W && d_Xtest && d_mean && d_var && d_ws && S >= 1 && M >= 0);
+  ARG_CHECK(h, E * d + E * E <= MFGP_SMALL - 1024);
+  if (M == 0) return 0;
+  // prior covariance between the E locations of one point (depends on the offsets only)
+  double h_kab[64];
+  for (int a = 0; a < E; a++)
+    for (int b = 0; b < E; b++) {
+      double r2 = 0.0;
+      for (int dd = 0; dd < d; dd++) {
+        const double t = (h_offsets[a * d + dd] - h_offsets[b * d + dd]) * tau;
+        r2 += t * t;
+      }
+      h_kab[a * E + b] = kl.c12 * exp(kl.ax * r2);
+    }
+  double* d_offs = h->d_scalars + 64;
+  double* d_kab = h->d_scalars + 1024;
+  CUDA_TRY(h, cudaMemcpyAsync(d_offs, h_offsets, (size_t)E * d * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(d_kab, h_kab, (size_t)E * E * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_info + 1, 0x7f, sizeof(int), h->stream));
+  const int npl = mfgp_padded_n(lf->N), nph = mfgp_padded_n(hf->N);
+  const int D = d + E, NP = E * (E + 1) / 2;
+  // scratch per test point (doubles); both stages reuse the same region, 2 x 128 columns of slack
+  const long long lf_pp = (long long)E * (d + 2LL * npl + 1) + NP;
+  const long long hf_pp = (long long)S * (D + nph + 2);
+  const long long keep_pp = (long long)E + E * E;                       // mu_l, Lc survive into the HF stage
+  const long long slack = 256LL * (2LL * npl + nph + D + 4);
+  const long long wsd = (long long)(ws_bytes / sizeof(double));
+  long long pm = (wsd - slack) / (keep_pp + (lf_pp > hf_pp ? lf_pp : hf_pp));
+  ARG_CHECK(h, pm >= 1);
+  if (pm > M) pm = M;
+  if (pm * E > (1LL << 30) / 4) pm = (1LL << 28) / E;
+  double* mu_l = d_ws;                    // (pm, E)
+  double* Lc = mu_l + pm * E;             // (pm, E, E)
+  double* rest = Lc + pm * E * E;
+  const int prof_saved = h->prof_on;
+  for (long long m_lo = 0; m_lo < M; m_lo += pm) {
+    const long long npts = (M - m_lo < pm) ? (M - m_lo) : pm;
+    {  // low-fidelity level: joint posterior at the npts*E locations
+      const long long cols = npts * E, cols_pad = (cols + 127) / 128 * 128;
+      double* locs = rest;                          // (cols, d)
+      double* Ks = locs + cols_pad * d;             // (cols_pad, npl)
+      double* T = Ks + cols_pad * npl;              // (npl, cols_pad)
+      double* G = T + cols_pad * npl;               // (npts, NP)
+      h->prof_on = 0;
+      if ((rc = build_locs_launch(h, d_Xtest + m_lo * d, npts, d, d_offs, E, tau, locs))) return rc;
+      if ((rc = cross_gen_launch(h, kl, lf->d_X, lf->N, npl, lf->d_alpha, locs, cols, cols_pad, Ks, mu_l)))
+        return rc;
+      if ((rc = trmm_store(h, lf->d_W, npl, Ks, cols_pad, T))) return rc;
+      if ((rc = group_gram_launch(h, T, npl, cols_pad, npts, E, G))) return rc;
+      if ((rc = joint_chol_launch(h, G, d_kab, npts, E, (include_lf_noise ? kl.noise : 0.0) + lf_jitter,
+                                  m0 + m_lo, Lc)))
+        return rc;
+      h->prof_on = prof_saved;
+    }
+    {  // high-fidelity level over (point, sample) columns
+      const long long ncols = npts * S, cols_pad = (ncols + 127) / 128 * 128;
+      double* Xq = rest;                            // (cols_pad, D)
+      double* mu_c = Xq + cols_pad * D;
+      double* ss = mu_c + cols_pad;
+      double* Ks = ss + cols_pad;                   // (cols_pad, nph)
+      if ((rc = build_mc_rows_joint_launch(h, d_Xtest, mu_l, Lc, d_eps, seed, m0, m_lo, ncols, S, d, E, Xq)))
+        return rc;
+      if ((rc = cross_gen_launch(h, kh, hf->d_X, hf->N, nph, hf->d_alpha, Xq, ncols, cols_pad, Ks, mu_c)))
+        return rc;
+      if ((rc = trmm_sumsq(h, hf->d_W, nph, Ks, cols_pad, ss))) return rc;
+      if ((rc = finish_var_launch(h, ss, ncols, kh.kdiag, include_hf_noise ? kh.noise : 0.0, ss))) return rc;
+      if ((rc = mc_aggregate_launch(h, mu_c, ss, npts, S, d_mean + m_lo, d_var + m_lo))) return rc;
+    }
+  }
+  if (h_wsum) {
+    if ((rc = wdot_launch(h, d_weights, d_mean, M, h->d_scalars + 20))) return rc;
+  }
+  if ((rc = fetch_scalars(h, 24))) return rc;
+  if (h_wsum) h_wsum[0] += h->h_pinned[20];
+  const int bad = h->h_info[1];
+  return (bad > 0 && bad < 0x7f7f7f7f) ? bad : 0;   // 1-based global index of the first non-PD joint covariance
 }
 
 int mfgp_fill_normal(mfgp_handle_t h, unsigned long long seed, long long first, long long count,

@@ -111,6 +111,8 @@ int lauum_padded(mfgp_ctx* h, const double* W, double* Kinv, int npad);
 int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad,
                double* out_ss);
 
+int trmm_store(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad, double* T);
+
 // ---- assemble.cu -------------------------------------------------------------------------
 int assemble_configure(mfgp_ctx* h);
 int assemble_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, double diag_add,

@@ -413,6 +413,15 @@ int lauum_padded(mfgp_ctx* h, const double* W, double* Kinv, int npad) {
   return launch_gemm<false, false>(h, p, PC_LAUUM);
 }
 
+// T[i][c] = sum_{k<=i} W[i][k] * Ks[c][k]   (T: npad x cols_pad, row-major, ld = cols_pad)
+int trmm_store(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad, double* T) {
+  ARG_CHECK(h, npad % LEAF == 0 && cols_pad % dg::Big::BN == 0 && cols_pad < (1LL << 31));
+  if (cols_pad == 0) return 0;
+  dg::GemmParams p = gp(W, npad, Ks, npad, T, cols_pad, npad, (int)cols_pad, npad, 1.0, 0.0);
+  p.ke_row = 1;
+  return launch_gemm<true, true>(h, p, PC_MISC);
+}
+
 int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad,
                double* out_ss) {
   ARG_CHECK(h, npad % LEAF == 0 && cols_pad % dg::Big::BN == 0);

@@ -282,6 +282,108 @@ __global__ void __launch_bounds__(256)
   for (int s = tid; s < S; s += 256) mu_c[(long long)blockIdx.x * S + s] = macc[s];
 }
 
+
+// ---- K7 with delays: joint low-fidelity posterior at the E augmented locations of a test point ----
+// G[p][a,b] = sum_i T[i][p*E+a] * T[i][p*E+b]  (packed lower triangle, a >= b); one thread per point,
+// rows of T are read coalesced (adjacent points are adjacent columns), fixed summation order.
+template <int E>
+__global__ void __launch_bounds__(128)
+    group_gram_kernel(const double* __restrict__ T, int npad, long long ldt, long long npts,
+                      double* __restrict__ G) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  constexpr int NP = E * (E + 1) / 2;
+  double acc[NP];
+#pragma unroll
+  for (int q = 0; q < NP; q++) acc[q] = 0.0;
+  const double* col = T + p * E;
+#pragma unroll 4
+  for (int i = 0; i < npad; i++) {
+    double v[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) v[e] = col[(long long)i * ldt + e];
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < E; a++)
+#pragma unroll
+      for (int b = 0; b <= a; b++, q++) acc[q] = fma(v[a], v[b], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < NP; q++) G[p * NP + q] = acc[q];
+}
+
+// cov = kab - G (diagonal clipped at 1e-15 like GPy's predictive variance, then + diag_add);
+// Lc[p] = chol(cov) (E x E, row-major lower).  A non-positive pivot records the point (1-based) in
+// info[1] (lowest index wins) and is replaced by 1e-300 so that the kernel finishes.
+template <int E>
+__global__ void __launch_bounds__(128)
+    joint_chol_kernel(const double* __restrict__ G, const double* __restrict__ kab, long long npts,
+                      double diag_add, long long p_global0, double* __restrict__ Lc, int* __restrict__ info) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  constexpr int NP = E * (E + 1) / 2;
+  double c[E][E];
+  int q = 0;
+#pragma unroll
+  for (int a = 0; a < E; a++)
+#pragma unroll
+    for (int b = 0; b <= a; b++, q++) {
+      double v = kab[a * E + b] - G[p * NP + q];
+      if (a == b) v = (v < 1e-15 ? 1e-15 : v) + diag_add;
+      c[a][b] = v;
+    }
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < E; j++) {
+    double dj = c[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) dj = fma(-c[j][k], c[j][k], dj);
+    if (!(dj > 0.0)) { bad = true; dj = 1e-300; }
+    const double lj = sqrt(dj);
+    c[j][j] = lj;
+#pragma unroll
+    for (int i = j + 1; i < E; i++) {
+      double v = c[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) v = fma(-c[i][k], c[j][k], v);
+      c[i][j] = v / lj;
+    }
+  }
+  if (bad) {
+    const long long idx = p_global0 + p + 1;
+    atomicMin(reinterpret_cast<unsigned*>(info + 1), (unsigned)(idx > 0x7fffffffLL ? 0x7fffffffLL : idx));
+  }
+#pragma unroll
+  for (int a = 0; a < E; a++)
+#pragma unroll
+    for (int b = 0; b < E; b++) Lc[(p * E + a) * E + b] = b <= a ? c[a][b] : 0.0;
+}
+
+// rows [x_m, mu_l[m] + Lc[m] eps] for columns c = (m - m_lo)*S + s of the current chunk;
+// eps: (M, S, E) supplied, or Philox counter ((m_global0 + m)*S + s)*E + e
+__global__ void build_mc_rows_joint_kernel(const double* __restrict__ Xtest, const double* __restrict__ mu_l,
+                                           const double* __restrict__ Lc, const double* __restrict__ eps,
+                                           unsigned long long seed, long long m_global0, long long m_lo,
+                                           long long ncols, int S, int d, int E,
+                                           double* __restrict__ out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  const long long pl = c / S;               // point within the chunk (mu_l / Lc are chunk-local)
+  const long long m = m_lo + pl;            // point within the call
+  const int s = (int)(c - pl * S);
+  double e[MFGP_MAX_E];
+  for (int b = 0; b < E; b++)
+    e[b] = eps ? eps[(m * S + s) * E + b]
+               : philox_normal((unsigned long long)(((m_global0 + m) * S + s) * E + b), seed);
+  double* row = out + c * (d + E);
+  for (int dd = 0; dd < d; dd++) row[dd] = Xtest[m * d + dd];
+  for (int a = 0; a < E; a++) {
+    double z = mu_l[pl * E + a];
+    for (int b = 0; b <= a; b++) z = fma(Lc[(pl * E + a) * E + b], e[b], z);
+    row[d + a] = z;
+  }
+}
+
 __global__ void zero_rows_kernel(double* __restrict__ p, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0.0;
@@ -597,6 +699,52 @@ int build_mc_rows_launch(mfgp_ctx* h, const double* Xtest, const double* mu_l, c
   if (ncols <= 0) return 0;
   build_mc_rows_kernel<<<nblk(ncols, 256), 256, 0, h->stream>>>(Xtest, mu_l, sd_l, eps, seed,
                                                                 m_global0, m_lo, ncols, S, d, out);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+
+int group_gram_launch(mfgp_ctx* h, const double* T, int npad, long long ldt, long long npts, int E, double* G) {
+  if (npts <= 0) return 0;
+#define MFGP_GG(E_)                                                                          \
+  case E_:                                                                                   \
+    group_gram_kernel<E_><<<nblk(npts, 128), 128, 0, h->stream>>>(T, npad, ldt, npts, G);   \
+    break;
+  switch (E) {
+    MFGP_GG(1) MFGP_GG(2) MFGP_GG(3) MFGP_GG(4) MFGP_GG(5) MFGP_GG(6) MFGP_GG(7) MFGP_GG(8)
+    default:
+      snprintf(h->err, sizeof(h->err), "joint low-fidelity sampling supports E <= 8 (got %d)", E);
+      return -1;
+  }
+#undef MFGP_GG
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int joint_chol_launch(mfgp_ctx* h, const double* G, const double* d_kab, long long npts, int E,
+                      double diag_add, long long p_global0, double* Lc) {
+  if (npts <= 0) return 0;
+#define MFGP_JC(E_)                                                                                     \
+  case E_:                                                                                              \
+    joint_chol_kernel<E_><<<nblk(npts, 128), 128, 0, h->stream>>>(G, d_kab, npts, diag_add, p_global0, \
+                                                                 Lc, h->d_info);                        \
+    break;
+  switch (E) {
+    MFGP_JC(1) MFGP_JC(2) MFGP_JC(3) MFGP_JC(4) MFGP_JC(5) MFGP_JC(6) MFGP_JC(7) MFGP_JC(8)
+    default:
+      return -1;
+  }
+#undef MFGP_JC
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int build_mc_rows_joint_launch(mfgp_ctx* h, const double* Xtest, const double* mu_l, const double* Lc,
+                               const double* eps, unsigned long long seed, long long m_global0,
+                               long long m_lo, long long ncols, int S, int d, int E, double* out) {
+  if (ncols <= 0) return 0;
+  build_mc_rows_joint_kernel<<<nblk(ncols, 256), 256, 0, h->stream>>>(Xtest, mu_l, Lc, eps, seed, m_global0,
+                                                                      m_lo, ncols, S, d, E, out);
   LAUNCH_CHECK(h);
   return 0;
 }

@@ -45,6 +45,25 @@ def test_assemble_matches_oracle(T, kind, d, E, N):
         assert util.rel_err(K, ref_g) < 1e-11
 
 
+@pytest.mark.parametrize("theta", [
+    [1e6, 0.02, 1e3, 0.05, 1e-8, 0.01, 1e-2],      # huge / tiny variances, length-scales far below the data spacing
+    [1e-150, 0.3, 1e-150, 0.3, 1e-300, 0.3, 1e-2],  # variances whose product underflows
+    [1.0, 1e-3, 1.0, 1e-3, 1.0, 1e-4, 0.0],         # exponents down to -1e8: every off-diagonal element underflows
+])
+def test_assemble_elementwise_accuracy_at_extreme_hyperparameters(T, theta):
+    """exp2s (fastmath.cuh) against the oracle element by element: relative error where the value is
+    representable, < 1e-300 absolute where it underflows (the clamp returns a tiny positive number)."""
+    X, _, _ = util.random_case(3, 300, 4, 1, go.KIND_COMPOSITE)
+    th = np.array(theta)
+    K = np.tril(T.ops.assemble(T.up(X), go.KIND_COMPOSITE, 4, th, uplo=0).cpu().numpy())
+    ref = np.tril(go.assemble_Ky(go.KIND_COMPOSITE, X, 4, th, form="direct"))
+    assert np.all(np.isfinite(K))
+    big = np.abs(ref) > 1e-290
+    # argument error |x| * 2^-52 for exponents up to ~700, plus ~2 ulp of the exponential itself
+    assert np.max(np.abs(K[big] - ref[big]) / np.abs(ref[big])) < 1e-12
+    assert np.max(np.abs(K[~big] - ref[~big]), initial=0.0) < 1e-289
+
+
 def test_assemble_odd_leading_dimension_and_jitter(T):
     X, _, th = util.random_case(1, 37, 2, 5, go.KIND_COMPOSITE)
     K = T.ops.assemble(T.up(X), go.KIND_COMPOSITE, 2, th, uplo=1, jitter=0.25, ld=41).cpu().numpy()

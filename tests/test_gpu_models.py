@@ -216,6 +216,72 @@ def test_mc_in_kernel_philox_matches_oracle_and_pce_mean(pkg):
     assert np.array_equal(mean2.cpu().numpy(), mean[128:, 0]) and np.array_equal(var2.cpu().numpy(), var[128:, 0])
 
 
+def _mc_delay_models(pkg, model, n_l=120, n_h=30, seed=7):
+    """GPDF / GPDFC in 2-D with delays (tau = 0.05, n = 2 -> E = 5, D = 7) on a data-driven LF GP."""
+    rs = np.random.RandomState(seed)
+    lf_X = rs.uniform(size=(n_l, 2))
+    hf_X = rs.uniform(size=(n_h, 2))
+    lf_theta = np.array([1.5, 0.4, 1e-3])
+    composite = model == "GPDFC"
+    theta = THETA_C if composite else THETA_R
+    m = getattr(pkg, model)(2, 0.05, 2, util.hf_2d, None, lf_X=lf_X, lf_Y=util.lf_2d(lf_X))
+    m.lf_model._set_params(lf_theta)
+    m.fit(hf_X, theta=theta)
+    o = mo.OracleMFGP(2, 2, 0.05, util.hf_2d, lf_X=lf_X, lf_Y=util.lf_2d(lf_X), lf_theta=lf_theta,
+                      use_composite_kernel=composite)
+    o.fit(hf_X, theta=theta)
+    return m, o
+
+
+@pytest.mark.parametrize("model", ["GPDF", "GPDFC"])
+def test_mc_with_delays_samples_the_joint_lf_posterior(pkg, model):
+    # SURVEY.md section 8a row A8 for E > 1: z_s = mu_l + chol(Sigma_l) eps_s with Sigma_l in R^(5x5)
+    m, o = _mc_delay_models(pkg, model)
+    M, S, E = 300, 40, 5
+    Xt = np.random.default_rng(8).uniform(size=(M, 2))
+    eps = np.random.default_rng(9).standard_normal((M, S, E))
+    mean, var = m.predict_mc(Xt, n_samples=S, eps=eps)
+    mu_ref, var_ref = o.predict_mc(Xt, eps)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+    assert util.rel_err(var, var_ref, 1.2) < 1e-6
+    # extra diagonal jitter on Sigma_l follows the oracle's
+    mean_j, var_j = m.predict_mc(Xt, n_samples=S, eps=eps, lf_jitter=1e-4)
+    mu_rj, var_rj = o.predict_mc(Xt, eps, jitter=1e-4)
+    assert util.rel_err(mean_j, mu_rj) < 1e-8 and util.rel_err(var_j, var_rj, 1.2) < 1e-6
+    assert util.rel_err(mean_j, mean) > 1e-7          # ... and it does change the result
+
+
+def test_mc_with_delays_one_sample_zero_eps_reproduces_predict(pkg):
+    m, o = _mc_delay_models(pkg, "GPDF")
+    Xt = np.random.default_rng(10).uniform(size=(257, 2))
+    mean, var = m.predict_mc(Xt, n_samples=1, eps=np.zeros((257, 1, 5)))
+    mu, v = m.predict(Xt)
+    assert util.rel_err(mean, mu) < 1e-12 and util.rel_err(var, v, 1.2) < 1e-10
+    mu_ref, _ = o.predict(Xt)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+
+
+def test_mc_with_delays_in_kernel_philox_and_sharding(pkg):
+    from multifidelity_datafusion_gps_b200 import ops
+    import torch
+    m, o = _mc_delay_models(pkg, "GPDF")
+    M, S, E, seed = 200, 16, 5, 11
+    Xt = np.random.default_rng(12).uniform(size=(M, 2))
+    mean, var = m.predict_mc(Xt, n_samples=S, seed=seed)
+    eps = ops.fill_normal(seed, 0, M * S * E, "cuda:0").cpu().numpy().reshape(M, S, E)
+    mu_ref, var_ref = o.predict_mc(Xt, eps)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+    assert util.rel_err(var, var_ref, 1.2) < 1e-6
+    # points [64, 200) alone with m0 = 64, and a scratch so small that the call runs in many chunks
+    dX = torch.from_numpy(Xt[64:]).to("cuda:0")
+    mean2, var2, _ = m.predict_mc_device(dX, S, None, seed, 64)
+    assert np.array_equal(mean2.cpu().numpy(), mean[64:, 0]) and np.array_equal(var2.cpu().numpy(), var[64:, 0])
+    small = 8 * (256 * (2 * 128 + 128 + 2 + 5 + 4) + 40 * (5 + 25 + max(5 * (2 + 256 + 1) + 15, S * (7 + 128 + 2))))
+    mean3, var3, _ = m.predict_mc_device(dX, S, None, seed, 64, ws_bytes=small)
+    assert np.array_equal(mean3.cpu().numpy(), mean2.cpu().numpy())
+    assert np.array_equal(var3.cpu().numpy(), var2.cpu().numpy())
+
+
 def test_assertions_mirror_reference(pkg):
     m = pkg.NARGP(2, util.hf_2d, util.lf_2d)
     with pytest.raises(AssertionError):
