@@ -166,6 +166,20 @@ int mfgp_fill_normal(mfgp_handle_t h, unsigned long long seed, long long first, 
  * h_val[0] = max_i v[i], h_idx[0] = lowest i attaining it (np.argmax semantics). */
 int mfgp_argmax(mfgp_handle_t h, const double* d_v, long long C, double* h_val, long long* h_idx);
 
+/* K9 -- polynomial-chaos projection on a quadrature grid.  Replaces
+ * cp.fit_quadrature / cp.E / cp.Var as src/gpc/chaospy_wrapper.py:18-29 uses them, for independent
+ * uniform inputs on the box [lb, ub] (tests/test_mfgp_adapt_4d.py:40) and the orthonormal Legendre basis:
+ *   coeff[k] = sum_q w_q f_q prod_i sqrt(2 k_i + 1) P_{k_i}(2 (x_qi - lb_i)/(ub_i - lb_i) - 1)
+ * so that mean = coeff[0] (the all-zero multi-index first) and variance = sum_{k>0} coeff[k]^2.
+ * d_nodes (Q, d), d_weights (Q) (summing to 1), d_values (Q): DEVICE.  h_multi_index: HOST (P, d)
+ * int32 degrees, each <= max_degree; P <= 4096.  d_coeff (P) DEVICE; h_coeff (P) HOST or NULL (when
+ * given the call synchronises).  d_ws / ws_bytes: scratch of at least mfgp_pce_ws_bytes(d, P). */
+size_t mfgp_pce_ws_bytes(int d, int P);
+int mfgp_pce_project(mfgp_handle_t h, const double* d_nodes, const double* h_lb, const double* h_ub,
+                     int d, const double* d_weights, const double* d_values, long long Q,
+                     const int* h_multi_index, int P, int max_degree, double* d_coeff,
+                     double* h_coeff, double* d_ws, size_t ws_bytes);
+
 #ifdef __cplusplus
 }
 #endif

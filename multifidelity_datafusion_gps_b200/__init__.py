@@ -9,6 +9,7 @@ from .abstractMFGP import AbstractMFGP
 from .adaptation_maximizers import AbstractMaximizer, CandidateSetMaximizer, ScipyDirectMaximizer
 from .augm_iterators import AbstractAugmIterator, BackwardAugmentation, EvenAugmentation
 from .models import GPDF, GPDFC, NARGP
+from . import gpc
 
 __all__ = ["MultifidelityDataFusion", "AbstractMFGP", "NARGP", "GPDF", "GPDFC", "AbstractMaximizer",
            "CandidateSetMaximizer", "ScipyDirectMaximizer", "AbstractAugmIterator",

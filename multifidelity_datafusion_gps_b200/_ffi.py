@@ -22,7 +22,7 @@ EXPORTS = [
     "mfgp_last_error", "mfgp_launch_count", "mfgp_profile_enable", "mfgp_profile_read", "mfgp_assemble", "mfgp_factorize", "mfgp_lml_grad",
     "mfgp_lml_grad_timed", "mfgp_potrf", "mfgp_trtri", "mfgp_lauum", "mfgp_predict_ws_bytes",
     "mfgp_predict", "mfgp_augment", "mfgp_predict_mc", "mfgp_predict_mc_delays", "mfgp_fill_normal",
-    "mfgp_argmax",
+    "mfgp_argmax", "mfgp_pce_ws_bytes", "mfgp_pce_project",
 ]
 
 
@@ -90,9 +90,12 @@ def load_library():
                                            vp, c_sz]
     lib.mfgp_fill_normal.argtypes = [vp, c_ull, c_ll, c_ll, vp]
     lib.mfgp_argmax.argtypes = [vp, vp, c_ll, vp, vp]
+    lib.mfgp_pce_ws_bytes.argtypes = [c_int, c_int]
+    lib.mfgp_pce_ws_bytes.restype = c_sz
+    lib.mfgp_pce_project.argtypes = [vp, vp, vp, vp, c_int, vp, vp, c_ll, vp, c_int, c_int, vp, vp, vp, c_sz]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("mfgp_last_error", "mfgp_launch_count", "mfgp_predict_ws_bytes"):
+        if name not in ("mfgp_last_error", "mfgp_launch_count", "mfgp_predict_ws_bytes", "mfgp_pce_ws_bytes"):
             fn.restype = c_int
     _lib = lib
     return lib

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmfgp_b200.so")
-SOURCES = ["capi.cu", "assemble.cu", "linalg.cu", "predict.cu"]
+SOURCES = ["capi.cu", "assemble.cu", "linalg.cu", "predict.cu", "pce.cu"]
 HEADERS = ["common.cuh", "gemm.cuh", "fastmath.cuh", os.path.join("..", "..", "include", "mfgp_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

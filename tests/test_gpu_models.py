@@ -315,3 +315,73 @@ def test_jitter_retry_on_duplicate_rows(pkg):
     assert model.last_jitter >= 0.0
     mu, _ = model.predict(X)
     assert util.rel_err(mu, Y) < 1e-3
+
+
+# ---- K9: PCE projection ------------------------------------------------
+@pytest.mark.parametrize("d,p,q", [(1, 0, 0), (1, 6, 9), (2, 5, 7), (3, 4, 4), (4, 8, 8), (5, 3, 3), (2, 20, 20)])
+def test_pce_projection_matches_oracle(pkg, d, p, q):
+    from oracle import pce_oracle as po
+    from multifidelity_datafusion_gps_b200.gpc import LegendrePCE
+    rng = np.random.default_rng(100 * d + p)
+    lb, ub = -rng.uniform(0.5, 1.5, d), rng.uniform(0.5, 2.0, d)
+    a = rng.uniform(0.5, 3.0, d)
+    f = lambda x: np.prod(np.sin(x * a + 0.3), axis=1) + 0.25 * x[:, 0] ** 2
+    pce = LegendrePCE(f, lb, ub, polynomial_order=p, quadrature_order=q)
+    pce.calculate_coefficients()
+    nodes, wts = po.tensor_grid(q + 1, lb, ub)
+    ref = po.project(nodes, wts, f(nodes), lb, ub, po.multi_index(d, p))
+    assert pce.coefficients.shape == ref.shape
+    assert util.rel_err(pce.coefficients, ref) < 1e-13
+    assert np.isclose(pce.get_mean(), ref[0], rtol=1e-13)
+    assert np.isclose(pce.get_var(), np.sum(ref[1:] ** 2), rtol=1e-12, atol=1e-300)
+
+
+def test_pce_reference_closed_forms_and_update_order(pkg):
+    # the reference's own gPC check: hf_4d = prod sin(pi x_i) + 5 on [0,1]^4 (tests/test_mfgp_adapt_4d.py:56-66)
+    from oracle import pce_oracle as po
+    from multifidelity_datafusion_gps_b200.gpc import LegendrePCE
+    pce = LegendrePCE(util.hf_4d, [0] * 4, [1] * 4, polynomial_order=4, quadrature_order=4)
+    pce.calculate_coefficients()
+    a4 = [np.pi] * 4
+    assert abs(pce.get_mean() - po.analytical_mean(a4, 5.0)) < 1e-5
+    pce.update_order(8)
+    pce.update_function(util.hf_4d)
+    assert abs(pce.get_mean() - po.analytical_mean(a4, 5.0)) < 1e-12
+    assert abs(pce.get_var() - po.analytical_var(a4)) < 1e-4 * po.analytical_var(a4)
+    assert pce.get_mean_var() == (pce.get_mean(), pce.get_var())
+
+
+def test_pce_of_the_model_mean_stays_on_device_and_matches_oracle(pkg):
+    from oracle import pce_oracle as po
+    from multifidelity_datafusion_gps_b200.gpc import LegendrePCE
+    m, o = _mc_models(pkg)
+    pce = LegendrePCE(m.predict, [0] * 4, [1] * 4, polynomial_order=5, quadrature_order=5)
+    pce.calculate_coefficients()                              # nodes -> K6 -> K9, no host round trip
+    mean_ref, var_ref, c_ref = po.pce_mean_var(lambda x: o.predict(x)[0], [0] * 4, [1] * 4, 5, 5)
+    assert util.rel_err(pce.coefficients, c_ref) < 1e-8
+    # the reference's way of wiring it (src/gpc/mfgp_gpc.py:25): a host lambda around predict
+    pce_host = LegendrePCE(lambda x: m.predict(x)[0], [0] * 4, [1] * 4, polynomial_order=5, quadrature_order=5)
+    pce_host.calculate_coefficients()
+    assert np.array_equal(pce_host.coefficients, pce.coefficients)
+    # MC-propagated mean through the device hook; its c_0 is the fused PCE mean of K7
+    f = lambda x: m.predict_mc(x, n_samples=8, seed=3)[0]
+    f.device_predict = lambda dX: m.predict_mc_device(dX, 8, None, 3, 0)[0]
+    pce_mc = LegendrePCE(f, [0] * 4, [1] * 4, polynomial_order=3, quadrature_order=3)
+    pce_mc.calculate_coefficients()
+    m.predict_mc(pce_mc.quad_points, n_samples=8, seed=3, weights=pce_mc.quad_weights)
+    assert np.isclose(pce_mc.get_mean(), m.last_pce_mean, rtol=1e-12)
+
+
+def test_mfgp_gpc_driver_runs_adaptation_rounds(pkg):
+    # src/gpc/mfgp_gpc.py: rounds of 5 adaptation steps, statistics re-projected after each round
+    from multifidelity_datafusion_gps_b200.gpc import LegendrePCE, MFGP_GPC
+    _, X_hf, X_test = _data(2)
+    cands = np.random.default_rng(1).uniform(size=(2000, 2))
+    m = pkg.NARGP(2, util.hf_2d, util.lf_2d, adapt_maximizer=pkg.CandidateSetMaximizer(cands))
+    m.fit(X_hf)
+    pce = LegendrePCE(m.predict, [0, 0], [1, 1], polynomial_order=6, quadrature_order=6)
+    drv = MFGP_GPC(m, pce, num_adapts=1, init_cost=5, X_test=X_test, Y_test=util.hf_2d(X_test))
+    drv.adapt()
+    assert len(drv.mean_history) == 2 and len(drv.var_history) == 2 and len(drv.mse_history) == 2
+    assert drv.cost_history == [5, 5 + m.adapt_steps]
+    assert m.hf_X.shape[0] == 5 + m.adapt_steps

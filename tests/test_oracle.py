@@ -168,3 +168,18 @@ def test_oracle_fit_recipe_improves_likelihood():
     before = m.log_likelihood()
     go.ard_recipe(m, 3, rng=np.random.RandomState(0))
     assert m.log_likelihood() > before
+
+
+def test_pce_oracle_reproduces_reference_closed_forms():
+    """oracle/pce_oracle.py against the closed-form mean / variance of prod sin(a_i x_i) on [0,1]^d that
+    the reference's own gPC tests are written around (tests/utils.py:14-27, tests/test_mfgp_adapt_2d.py:9)."""
+    from oracle import pce_oracle as po
+    a2 = [2.2 * np.pi, np.pi]
+    m, v, c = po.pce_mean_var(lambda x: np.prod(np.sin(x * np.array(a2)), axis=1), [0, 0], [1, 1], 14, 14)
+    assert abs(m - po.analytical_mean(a2)) < 1e-14
+    assert abs(v - po.analytical_var(a2)) < 1e-9 * po.analytical_var(a2)
+    a4 = [np.pi] * 4                                      # tests/test_mfgp_adapt_4d.py:10,13-15 (constant 5)
+    m, v, c = po.pce_mean_var(lambda x: np.prod(np.sin(x * np.pi), axis=1) + 5.0, [0] * 4, [1] * 4, 8, 8)
+    assert abs(m - po.analytical_mean(a4, 5.0)) < 1e-12
+    assert abs(v - po.analytical_var(a4)) < 1e-4 * po.analytical_var(a4)      # truncation at order 8
+    assert c.shape == (495,)                               # C(8 + 4, 4) terms of total degree <= 8
