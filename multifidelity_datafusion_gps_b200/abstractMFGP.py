@@ -18,6 +18,7 @@ from .adaptation_maximizers import AbstractMaximizer
 
 
 class AbstractMFGP(metaclass=abc.ABCMeta):
+    parallel_restarts = False     # set True to spread optimize_restarts over the ranks
 
     @abc.abstractmethod
     def __init__(self, name: str, input_dim: int, num_derivatives: int, tau: float, f_exact: callable,
@@ -101,7 +102,10 @@ class AbstractMFGP(metaclass=abc.ABCMeta):
         model.optimize(max_iters=500)
         model[".*Gaussian_noise"].unfix()
         model[".*Gaussian_noise"].constrain_positive()
-        model.optimize_restarts(num_restarts, optimizer="bfgs", max_iters=1000, verbose=False)
+        # parallel_restarts: under torch.distributed every rank calls fit() collectively and takes a
+        # share of the independent restarts (gp.GPRegression._optimize_restarts_distributed)
+        model.optimize_restarts(num_restarts, optimizer="bfgs", max_iters=1000, verbose=False,
+                                parallel=getattr(self, "parallel_restarts", False))
 
     # -- adaptation loop --------------------------------------------------------------------------
     def adapt_and_plot(self, plot_means: bool = False, plot_uncertainties: bool = False,

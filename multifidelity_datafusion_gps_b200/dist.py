@@ -52,6 +52,32 @@ def gather_argmax(local_val, local_idx, device=None):
     return combine_argmax([t.item() for t in vs], [t.item() for t in is_])
 
 
+def restart_share(num_restarts, rank, world):
+    """Restart indices rank `rank` runs: round-robin, so that run 0 (the warm start) is on rank 0."""
+    return [i for i in range(int(num_restarts)) if i % int(world) == int(rank)]
+
+
+def gather_runs(local_runs):
+    """all_gather of per-rank lists of (run index, objective, x_opt) -> one list ordered by run index
+    on every rank.  Small host objects; the object channel is enough (no data-path collective)."""
+    if not is_dist():
+        return sorted(local_runs, key=lambda r: r[0])
+    gathered = [None] * tdist.get_world_size()
+    tdist.all_gather_object(gathered, list(local_runs))
+    return sorted((r for part in gathered for r in part), key=lambda r: r[0])
+
+
+def best_run(runs):
+    """np.argmin semantics over runs ordered by index: lowest objective, lowest run index on ties;
+    NaN objectives never win unless every run is NaN."""
+    best = None
+    for r in sorted(runs, key=lambda r: r[0]):
+        f = r[1]
+        if best is None or (f < best[1]) or (best[1] != best[1] and f == f):
+            best = r
+    return best
+
+
 def broadcast_tensors(tensors, src=0):
     if not is_dist():
         return

@@ -309,6 +309,10 @@ class GPRegression:
         free = ~self._fixed
         kwargs.pop("optimizer", None)      # 'bfgs' resolves to L-BFGS-B in paramz.get_optimizer
         first = len(self.optimization_runs)
+        from . import dist
+        rank, world = dist.rank_world()
+        if parallel and world > 1:
+            return self._optimize_restarts_distributed(num_restarts, robust, rank, world, **kwargs)
         for i in range(num_restarts):
             try:
                 if i > 0:
@@ -326,6 +330,39 @@ class GPRegression:
             theta = self.param_array
             theta[free] = logexp_f(runs[best][0])
             self._set_params(theta)
+        return self
+
+    def _optimize_restarts_distributed(self, num_restarts, robust, rank, world, **kwargs):
+        """The restarts of optimize_restarts are independent (src/abstractMFGP.py:137): with
+        ``parallel=True`` under torch.distributed, rank r runs the restarts i = r (mod world) on its own
+        GPU and the best run is agreed on through one all_gather of (index, objective, x_opt).
+        Every rank draws ALL starting points from the global NumPy RNG in the serial order, so with the
+        same RNG state on every rank the result equals the serial loop's (each L-BFGS-B run is
+        deterministic given its start), and every rank ends in the same state."""
+        from . import dist
+        free = ~self._fixed
+        nfree = int(free.sum())
+        starts = [None] + [np.random.normal(size=nfree) for _ in range(1, num_restarts)]
+        theta0 = self.param_array.copy()
+        local = []
+        for i in dist.restart_share(num_restarts, rank, world):
+            try:
+                theta = theta0.copy()
+                if i > 0:
+                    theta[free] = logexp_f(starts[i])
+                self._set_params(theta)
+                self.optimize(**kwargs)
+                x_opt, f_opt = self.optimization_runs.pop()
+                local.append((i, float(f_opt), np.asarray(x_opt, dtype=np.float64)))
+            except Exception:
+                if not robust:
+                    raise
+        runs = dist.gather_runs(local)
+        self.optimization_runs.extend((x, f) for _, f, x in runs)
+        theta = theta0.copy()
+        if runs:
+            theta[free] = logexp_f(dist.best_run(runs)[2])
+        self._set_params(theta)
         return self
 
     # -- prediction ----------------------------------------------------------------------------

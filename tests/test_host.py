@@ -156,3 +156,65 @@ def test_sharded_argmax_world_size_2_gloo():
     for rank, idx, val, ref_idx, ref_val, total, ref_total in res:
         assert idx == ref_idx and val == ref_val           # shard-count invariant, bit-exact
         assert np.isclose(total, ref_total, rtol=1e-12)
+
+
+# ---- restart-parallel fit: host protocol on gloo ----------------------
+def _stub_gp():
+    """gp.GPRegression with the GPU objective replaced by a multi-modal host function of the
+    transformed parameters: the restart protocol (RNG order, shares, gather, winner) is what is tested."""
+    import scipy.optimize as sopt
+    from multifidelity_datafusion_gps_b200 import gp
+
+    class Stub(gp.GPRegression):
+        def __init__(self):                      # no device, no kernels
+            self._theta = np.ones(3)
+            self._fixed = np.zeros(3, dtype=bool)
+            self.optimization_runs = []
+
+        @property
+        def param_array(self):
+            return self._theta.copy()
+
+        def _set_params(self, theta):
+            self._theta = np.asarray(theta, dtype=np.float64).copy()
+
+        def optimize(self, optimizer=None, max_iters=1000, messages=False, **kw):
+            f = lambda x: (float(np.sum(np.sin(3.0 * x) + 0.1 * x ** 2)), 3.0 * np.cos(3.0 * x) + 0.2 * x)
+            x0 = gp.logexp_finv(self.param_array)
+            x_opt, f_opt, _ = sopt.fmin_l_bfgs_b(f, x0, maxfun=max_iters, maxiter=max_iters)
+            self._set_params(gp.logexp_f(x_opt))
+            self.optimization_runs.append((x_opt, float(f_opt)))
+            return self
+    return Stub()
+
+
+def _restart_worker(rank, world, port, q):
+    import torch.distributed as tdist
+    tdist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    np.random.seed(123)                          # same RNG state on every rank (documented requirement)
+    m = _stub_gp()
+    m.optimize_restarts(7, parallel=True, max_iters=200)
+    q.put((rank, m.param_array, [f for _, f in m.optimization_runs]))
+    tdist.destroy_process_group()
+
+
+def test_restart_parallel_fit_world_size_2_gloo_equals_serial():
+    import torch.multiprocessing as mp
+    from multifidelity_datafusion_gps_b200 import dist
+    assert dist.restart_share(7, 0, 2) == [0, 2, 4, 6] and dist.restart_share(7, 1, 2) == [1, 3, 5]
+    assert dist.best_run([(0, 2.0, "a"), (1, 1.0, "b"), (2, 1.0, "c"), (3, float("nan"), "d")])[2] == "b"
+    np.random.seed(123)
+    serial = _stub_gp()
+    serial.optimize_restarts(7, max_iters=200)   # world size 1: the reference's serial loop
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_restart_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, theta, objs in res:
+        assert np.array_equal(theta, serial.param_array)              # same winner, bit for bit
+        assert objs == [f for _, f in serial.optimization_runs]       # same runs, in run order
