@@ -110,6 +110,20 @@ int mfgp_lml_grad_timed(mfgp_handle_t h, int kind, const double* d_X, const doub
                         int D, int d, const double* h_theta, int P, double jitter, double* d_A,
                         double* d_W, double* d_alpha, double* h_lml, double* h_grad, double* h_ms);
 
+/* Bordered update at FIXED theta: one training point appended, as the
+ * adaptation loop does once per step (src/abstractMFGP.py:320,354), in O(N^2) instead of refactorising:
+ *   l = W k, L[N] = [l, l_nn], l_nn = sqrt(K(a,a) + noise + 1e-8 + jitter - |l|^2),
+ *   W[N] = [-(W^T l)/l_nn, 1/l_nn], alpha = W^T (W y).
+ * d_X (N+1, D) and d_y (N+1): the new point is row N; N is the OLD count.  d_A, d_W, d_alpha are sized
+ * for the N+1 points, Npad' = mfgp_padded_n(N+1): when N is a multiple of 128 the caller first moves
+ * the factors into buffers one 128-tile larger (identity on the new pad diagonal, zeros elsewhere).
+ * d_W must hold L^-1 of the N points; a_holds_L != 0 iff d_A holds L (after mfgp_factorize; after mfgp_lml_grad it holds K^-1): row N
+ * of L is then written and h_out[0..1] = {LML, logdet} of the N+1 points, else they are NaN.
+ * h_out[2] = y^T alpha, h_out[3] = l_nn.  Returns N+1 if the new pivot is not positive. */
+int mfgp_append_point(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N, int D,
+                      int d, const double* h_theta, int P, double jitter, double* d_A, double* d_W,
+                      double* d_alpha, int a_holds_L, double* h_out);
+
 /* Building blocks exposed for the parity tests (LAPACK names, lower, row-major, n multiple of 128). */
 int mfgp_potrf(mfgp_handle_t h, double* d_A, double* d_W, int npad);   /* A -> L; W diag blocks -> leaf inverses */
 int mfgp_trtri(mfgp_handle_t h, const double* d_L, double* d_W, int npad); /* completes W = L^-1 (after mfgp_potrf) */

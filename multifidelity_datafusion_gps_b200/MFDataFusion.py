@@ -64,6 +64,15 @@ class MultifidelityDataFusion(AbstractMFGP):
         else:
             self.hf_model._set_params(np.asarray(theta, dtype=np.float64))
 
+    def _append_hf_point(self, new_hf_X):
+        """Last row of new_hf_X joins the high-fidelity GP at fixed hyper-parameters: O(N^2) bordered
+        update of (L, L^-1, alpha) on the GPU (gp.GPRegression.append_point) instead of a refit."""
+        x = np.atleast_2d(new_hf_X[-1])
+        y = np.asarray(self.f_exact(x), dtype=np.float64).reshape(1, 1)
+        self.hf_X = new_hf_X
+        self.hf_Y = np.vstack((self.hf_Y, y))
+        self.hf_model.append_point(self.__augment_Data(x), y)
+
     # -- A10 adapt --------------------------------------------------------------------------------
     def adapt(self, adapt_steps: int, plot_mode: str = None, X_test: np.ndarray = None,
               Y_test: np.ndarray = None, eps: float = 1e-8):

@@ -20,7 +20,7 @@ TILE = 128
 EXPORTS = [
     "mfgp_version", "mfgp_padded_n", "mfgp_create", "mfgp_destroy", "mfgp_set_stream",
     "mfgp_last_error", "mfgp_launch_count", "mfgp_profile_enable", "mfgp_profile_read", "mfgp_assemble", "mfgp_factorize", "mfgp_lml_grad",
-    "mfgp_lml_grad_timed", "mfgp_potrf", "mfgp_trtri", "mfgp_lauum", "mfgp_predict_ws_bytes",
+    "mfgp_lml_grad_timed", "mfgp_append_point", "mfgp_potrf", "mfgp_trtri", "mfgp_lauum", "mfgp_predict_ws_bytes",
     "mfgp_predict", "mfgp_augment", "mfgp_predict_mc", "mfgp_predict_mc_delays", "mfgp_fill_normal",
     "mfgp_argmax", "mfgp_pce_ws_bytes", "mfgp_pce_project",
 ]
@@ -74,6 +74,7 @@ def load_library():
     lib.mfgp_profile_read.argtypes = [vp, vp, vp]
     lib.mfgp_assemble.argtypes = [vp, c_int, vp, c_int, c_int, c_int, vp, c_int, c_dbl, vp, c_ll, c_int]
     lib.mfgp_factorize.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, c_dbl, vp, vp, vp, vp]
+    lib.mfgp_append_point.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, c_dbl, vp, vp, vp, c_int, vp]
     lib.mfgp_lml_grad.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, c_dbl, vp, vp, vp, vp, vp]
     lib.mfgp_lml_grad_timed.argtypes = lib.mfgp_lml_grad.argtypes + [vp]
     lib.mfgp_potrf.argtypes = [vp, vp, vp, c_int]

@@ -19,6 +19,11 @@ from .adaptation_maximizers import AbstractMaximizer
 
 class AbstractMFGP(metaclass=abc.ABCMeta):
     parallel_restarts = False     # set True to spread optimize_restarts over the ranks
+    refit_every = 1               # adaptation steps per hyper-parameter refit
+
+    def _append_hf_point(self, new_hf_X):
+        """One acquired point at fixed hyper-parameters; models without an incremental path refit."""
+        self.fit(new_hf_X)
 
     @abc.abstractmethod
     def __init__(self, name: str, input_dim: int, num_derivatives: int, tau: float, f_exact: callable,
@@ -122,7 +127,12 @@ class AbstractMFGP(metaclass=abc.ABCMeta):
             if plot_error or plot_uncertainties:
                 if self.X_test is not None and self.Y_test is not None:
                     self.mse_history.append(self.get_mse(self.X_test, self.Y_test))
-            self.fit(new_hf_X)
+            # refit_every = 1 is the reference's loop (refit after every acquisition, :354); k > 1 keeps
+            # the hyper-parameters for k-1 steps and extends the factorisation by a bordered update
+            if (i + 1) % max(1, int(getattr(self, "refit_every", 1))) == 0:
+                self.fit(new_hf_X)
+            else:
+                self._append_hf_point(new_hf_X)
             if np.abs(fopt) < self.eps:
                 self.adapt_steps = i + 1
                 print("Iteration stopped after {} iterations!".format(i + 1)

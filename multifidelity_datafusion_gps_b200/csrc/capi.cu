@@ -24,6 +24,8 @@ int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, 
                         const double* sd_l, const double* eps, unsigned long long seed,
                         long long m_global0, long long m_lo, long long npts, int S,
                         long long cols_pad, double* Ks, double* mu_c);
+int append_point_launch(mfgp_ctx* h, const double* k, int N, int npad, double kaa, double* A, double* W,
+                        int write_L, double* l_tmp, double* t_tmp, double* d_out2);
 int mc_max_samples();
 int predict_configure(mfgp_ctx* h);
 int sqrt_launch(mfgp_ctx* h, double* v, long long n);
@@ -335,6 +337,36 @@ int mfgp_lml_grad(mfgp_handle_t h, int kind, const double* d_X, const double* d_
                   double* d_alpha, double* h_lml, double* h_grad) {
   return mfgp_lml_grad_timed(h, kind, d_X, d_y, N, D, d, h_theta, P, jitter, d_A, d_W, d_alpha,
                              h_lml, h_grad, nullptr);
+}
+
+int mfgp_append_point(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N, int D,
+                      int d, const double* h_theta, int P, double jitter, double* d_A, double* d_W,
+                      double* d_alpha, int a_holds_L, double* h_out) {
+  ENTER(h);
+  ARG_CHECK(h, d_X && d_y && d_A && d_W && d_alpha && N >= 1);
+  KParams kp;
+  int rc = make_kparams(h, kind, D, d, h_theta, P, &kp);
+  if (rc) return rc;
+  const int npad = mfgp_padded_n(N + 1);   // the buffers are sized for the N+1 points
+  ARG_CHECK(h, 3LL * npad <= MFGP_PARTIALS);
+  double* krow = h->d_partials;
+  double* l_tmp = krow + npad;
+  double* t_tmp = l_tmp + npad;
+  CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, sizeof(int), h->stream));
+  // k = K(x_new, X[0:N]) (zero on the pad); the new point is row N of d_X
+  if ((rc = cross_gen_launch(h, kp, d_X, N, npad, d_alpha, d_X + (long long)N * D, 1, 1, krow, nullptr))) return rc;
+  if ((rc = append_point_launch(h, krow, N, npad, kp.kdiag + kp.noise + JITTER_CONST + jitter, d_A, d_W,
+                                a_holds_L, l_tmp, t_tmp, h->d_scalars + 32)))
+    return rc;
+  if ((rc = solve_alpha_launch(h, d_A, d_W, npad, N + 1, d_y, h->d_partials, d_alpha, h->d_scalars))) return rc;
+  if ((rc = fetch_scalars(h, 40))) return rc;
+  if (h_out) {
+    h_out[0] = a_holds_L ? h->h_pinned[0] : NAN;   // LML of the N+1 points
+    h_out[1] = a_holds_L ? h->h_pinned[1] : NAN;   // logdet
+    h_out[2] = h->h_pinned[2];                     // y^T alpha
+    h_out[3] = h->h_pinned[32];                    // new diagonal entry of L
+  }
+  return h->h_info[0];
 }
 
 int mfgp_potrf(mfgp_handle_t h, double* d_A, double* d_W, int npad) {

@@ -590,6 +590,52 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+
+// Bordered Cholesky update (one appended training point, fixed theta):
+//   l = W k (done), t = W^T l (done);  s = K(a,a) + diag_add - |l|^2;  L[N] = [l, sqrt(s)];
+//   W[N] = [-t / sqrt(s), 1 / sqrt(s)].   Single block; the sum runs in a fixed order.
+__global__ void __launch_bounds__(256)
+    append_finish_kernel(const double* __restrict__ l, const double* __restrict__ t, int N, int npad,
+                         double kaa, double* __restrict__ A, double* __restrict__ W, int write_L,
+                         int* __restrict__ info, double* __restrict__ out /* [0] = l_nn, [1] = s */) {
+  __shared__ double sv[256];
+  __shared__ double s_lnn;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) acc = fma(l[i], l[i], acc);
+  sv[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sv[threadIdx.x] += sv[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double s = kaa - sv[0];
+    if (!(s > 0.0)) {
+      info[0] = N + 1;
+      s = 1.0;
+    }
+    s_lnn = sqrt(s);
+    out[0] = s_lnn;
+    out[1] = s;
+  }
+  __syncthreads();
+  const double lnn = s_lnn, rinv = 1.0 / lnn;
+  double* Arow = A + (long)N * npad;
+  double* Wrow = W + (long)N * npad;
+  for (int j = threadIdx.x; j < npad; j += 256) {
+    if (j < N) {
+      if (write_L) Arow[j] = l[j];
+      Wrow[j] = -t[j] * rinv;
+    } else if (j == N) {
+      if (write_L) Arow[j] = lnn;
+      Wrow[j] = rinv;
+    } else {
+      if (write_L) Arow[j] = 0.0;
+      Wrow[j] = 0.0;
+    }
+  }
+}
+
 inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
 }  // namespace
@@ -602,6 +648,19 @@ int solve_alpha_launch(mfgp_ctx* h, const double* L, const double* W, int npad, 
   trmv_lower_t_kernel<<<npad / 32, 256, 0, h->stream>>>(W, npad, v_tmp, alpha);
   LAUNCH_CHECK(h);
   lml_kernel<<<1, 256, 0, h->stream>>>(L, npad, N, y, alpha, d_out3);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+
+// l = W k and t = W^T l for the bordered update, then the finishing kernel
+int append_point_launch(mfgp_ctx* h, const double* k, int N, int npad, double kaa, double* A, double* W,
+                        int write_L, double* l_tmp, double* t_tmp, double* d_out2) {
+  trmv_lower_kernel<<<nblk(npad, 8), 256, 0, h->stream>>>(W, npad, k, N, l_tmp);
+  LAUNCH_CHECK(h);
+  trmv_lower_t_kernel<<<npad / 32, 256, 0, h->stream>>>(W, npad, l_tmp, t_tmp);
+  LAUNCH_CHECK(h);
+  append_finish_kernel<<<1, 256, 0, h->stream>>>(l_tmp, t_tmp, N, npad, kaa, A, W, write_L, h->d_info, d_out2);
   LAUNCH_CHECK(h);
   return 0;
 }

@@ -18,7 +18,7 @@ import torch
 from scipy import optimize as _sopt
 
 from . import _ffi
-from ._ffi import KIND_COMPOSITE, KIND_RBF, MfgpError, NotPositiveDefinite, padded_n
+from ._ffi import TILE, KIND_COMPOSITE, KIND_RBF, MfgpError, NotPositiveDefinite, padded_n
 
 _LIM_VAL = 36.0
 _LOG_LIM_VAL = float(np.log(np.finfo(np.float64).max))
@@ -171,6 +171,7 @@ class GPRegression:
         self.optimization_runs = []
         self._theta_c = (ctypes.c_double * 8)()
         self.last_jitter = 0.0
+        self._a_holds_L = False
 
     # -- parameters ------------------------------------------------------------------------
     @property
@@ -249,6 +250,7 @@ class GPRegression:
             timings[:] = [ms[i] for i in range(6)]
         self._post_theta = theta.copy()
         self._dirty = not np.array_equal(theta, self.param_array)
+        self._a_holds_L = False                     # d_A now holds K^-1
         return lml.value, np.array([grad[i] for i in range(P)])
 
     def _ensure_posterior(self):
@@ -268,6 +270,48 @@ class GPRegression:
         self._call_with_jitter(run, theta)
         self._lml = out[0]
         self._dirty = False
+        self._a_holds_L = True
+
+    def append_point(self, x_row, y):
+        """Append one training point at FIXED hyper-parameters with the O(N^2) bordered update
+        (mfgp_append_point) instead of refactorising: what one adaptation step adds
+        (src/abstractMFGP.py:320,354) when the hyper-parameters are not re-optimised."""
+        self._ensure_posterior()
+        h = _ffi.get_handle(self.device)
+        x_row = np.asarray(x_row, dtype=np.float64).reshape(1, self.D)
+        self.X = np.vstack([self.X, x_row])
+        self.Y = np.vstack([self.Y, np.asarray(y, dtype=np.float64).reshape(1, 1)])
+        self._dX = to_device(self.X, self.device)
+        self._dy = to_device(self.Y.ravel(), self.device)
+        if self.N % TILE == 0:                       # padded buffers are full: add one 128-tile
+            old, new = self.npad, self.npad + TILE
+            dev = self._dA.device
+            for name in ("_dA", "_dW"):
+                buf = torch.zeros((new, new), dtype=torch.float64, device=dev)
+                buf[:old, :old] = getattr(self, name)
+                idx = torch.arange(old, new, device=dev)
+                buf[idx, idx] = 1.0                  # identity pad block
+                setattr(self, name, buf)
+            alpha = torch.zeros(new, dtype=torch.float64, device=dev)
+            alpha[:old] = self._dalpha
+            self._dalpha = alpha
+            self.npad = new
+        theta = self.param_array
+        out = (ctypes.c_double * 4)()
+        rc = h.lib.mfgp_append_point(
+            h.h, self.kern.kind, self._dX.data_ptr(), self._dy.data_ptr(), self.N, self.D, self.kern.d,
+            self._theta_ptr(theta), len(theta), float(self.last_jitter), self._dA.data_ptr(),
+            self._dW.data_ptr(), self._dalpha.data_ptr(), int(self._a_holds_L),
+            ctypes.cast(out, ctypes.c_void_p))
+        self.N += 1
+        if rc != 0:                                  # new pivot not positive (or failure): refactorise
+            if rc < 0:
+                h.check(rc)
+            self._dirty = True
+            self._ensure_posterior()
+            return self
+        self._lml = out[0]
+        return self
 
     def log_likelihood(self):
         self._dirty = True
@@ -282,7 +326,13 @@ class GPRegression:
         theta[free] = logexp_f(x)
         self._set_params(theta)
         try:
+            # a line search that left the representable range (NaN, or a softplus that underflowed to 0)
+            # is an infeasible point like a failed factorisation (paramz counts both as failures)
+            if not (np.all(np.isfinite(theta)) and np.all(theta[:-1] > 0.0) and theta[-1] >= 0.0):
+                raise NotPositiveDefinite(0)
             lml, g = self.lml_and_grad(theta)
+            if not (np.isfinite(lml) and np.all(np.isfinite(g))):
+                raise NotPositiveDefinite(0)
             self._fail_count = 0
         except NotPositiveDefinite:
             if self._fail_count >= 10:

@@ -262,3 +262,32 @@ def test_large_factorization_properties(T):
         lm = T.ops.factorize(dX, dy, kind, d, tm, buf)[0]
         fd = (lp - lm) / (2 * hstep)
         assert abs(g[i] - fd) <= 1e-5 * max(1.0, abs(fd))
+
+
+@pytest.mark.parametrize("kind,d,E", [(go.KIND_COMPOSITE, 2, 1), (go.KIND_RBF, 3, 0)])
+@pytest.mark.parametrize("N0", [5, 127, 128, 200])
+def test_bordered_update_matches_refactorisation(T, kind, d, E, N0):
+    """mfgp_append_point through gp.GPRegression.append_point: three points appended one by one at fixed
+    theta (crossing a 128-tile boundary for N0 = 127, 128) against the oracle's factorisation of all points."""
+    from multifidelity_datafusion_gps_b200 import gp
+    X, Y, th = util.random_case(11, N0 + 3, d, E, kind)
+    kern = gp.NARGPKernel(d, E) if kind == go.KIND_COMPOSITE else gp.RBF(d + E)
+    m = gp.GPRegression(X[:N0], Y[:N0], kernel=kern)
+    m._set_params(th)
+    m.predict(X[:2])                                   # factorise the first N0 points
+    for i in range(N0, N0 + 3):
+        m.append_point(X[i], Y[i])
+    assert m.N == N0 + 3 and m.npad == (N0 + 3 + 127) // 128 * 128
+    ref = go.OracleGPRegression(X, Y, kind=kind, d=d, theta=th, form="direct")
+    L_ref, alpha_ref = ref.posterior()
+    n = N0 + 3
+    assert util.rel_err(m._dalpha.cpu().numpy()[:n], alpha_ref.ravel()) < 1e-9
+    assert np.all(m._dalpha.cpu().numpy()[n:] == 0.0)
+    assert util.rel_err(np.tril(m._dA.cpu().numpy()[:n, :n]), L_ref) < 1e-11
+    W = np.tril(m._dW.cpu().numpy()[:n, :n])             # blocks above the diagonal are trtri scratch
+    assert util.rel_err(W @ L_ref, np.eye(n)) < 1e-9
+    assert np.isclose(m._lml, ref.log_likelihood(), rtol=1e-9)
+    Xq = np.random.default_rng(12).uniform(size=(64, d + E))
+    mu, var = m.predict(Xq)
+    mu_ref, var_ref = ref.predict(Xq)
+    assert util.rel_err(mu, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.5) < 1e-6

@@ -385,3 +385,23 @@ def test_mfgp_gpc_driver_runs_adaptation_rounds(pkg):
     assert len(drv.mean_history) == 2 and len(drv.var_history) == 2 and len(drv.mse_history) == 2
     assert drv.cost_history == [5, 5 + m.adapt_steps]
     assert m.hf_X.shape[0] == 5 + m.adapt_steps
+
+
+def test_adaptation_with_bordered_updates_between_refits(pkg):
+    # refit_every = 3: steps 1, 2 extend the factorisation at fixed theta, step 3 refits
+    _, X_hf, X_test = _data(2)
+    cands = np.random.default_rng(2).uniform(size=(3000, 2))
+    m = pkg.NARGP(2, util.hf_2d, util.lf_2d, adapt_maximizer=pkg.CandidateSetMaximizer(cands))
+    m.refit_every = 3
+    m.fit(X_hf)
+    theta0 = m.hf_model.param_array.copy()
+    m.adapt(2)                                                    # two bordered updates, no refit
+    assert m.hf_X.shape == (7, 2) and m.hf_Y.shape == (7, 1) and m.hf_model.N == 7
+    assert np.array_equal(m.hf_model.param_array, theta0)
+    o = mo.OracleMFGP(2, 0, 0, util.hf_2d, f_low=util.lf_2d)
+    o.fit(m.hf_X, theta=theta0)                                   # full factorisation of the same 7 points
+    mean, var = m.predict(X_test)
+    mu_ref, var_ref = o.predict(X_test)
+    assert util.rel_err(mean, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.2) < 1e-6
+    m.adapt(3)                                                    # third step of this call refits
+    assert m.hf_model.N == 10 and not np.array_equal(m.hf_model.param_array, theta0)
