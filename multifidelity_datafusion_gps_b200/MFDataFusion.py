@@ -34,7 +34,7 @@ class MultifidelityDataFusion(AbstractMFGP):
                  lower_bound: np.ndarray = None, upper_bound: float = None, f_low: callable = None,
                  lf_X: np.ndarray = None, lf_Y: np.ndarray = None, lf_hf_adapt_ratio: int = 1,
                  use_composite_kernel: bool = True, adapt_maximizer: AbstractMaximizer = None,
-                 eps: float = 1e-8, add_noise: bool = False):
+                 eps: float = 1e-8, add_noise: bool = False, augm_iterator=None):
         if adapt_maximizer is None:
             adapt_maximizer = ScipyDirectMaximizer()      # the reference's default (:59)
         super().__init__(name=name, input_dim=input_dim, num_derivatives=num_derivatives, tau=tau,
@@ -42,7 +42,18 @@ class MultifidelityDataFusion(AbstractMFGP):
                          lf_X=lf_X, lf_Y=lf_Y, lf_hf_adapt_ratio=lf_hf_adapt_ratio,
                          use_composite_kernel=use_composite_kernel, adapt_maximizer=adapt_maximizer,
                          eps=eps)
-        self.augm_iterator = BackwardAugmentation(self.num_derivatives, dim=input_dim)
+        # The reference hard-wires BackwardAugmentation here (:67) although it ships EvenAugmentation too
+        # (src/augm_iterators/even_augm_iterator.py); `augm_iterator` (extension) selects the delay
+        # pattern: None / "backward", "even", an AbstractAugmIterator class or a ready instance.
+        if augm_iterator is None or augm_iterator == "backward":
+            augm_iterator = BackwardAugmentation
+        elif augm_iterator == "even":
+            from .augm_iterators import EvenAugmentation
+            augm_iterator = EvenAugmentation
+        if isinstance(augm_iterator, type):
+            augm_iterator = augm_iterator(self.num_derivatives, dim=input_dim)
+        assert augm_iterator.dim == input_dim, "delay iterator / input dimension mismatch"
+        self.augm_iterator = augm_iterator
         self.initialize_kernel(use_composite_kernel)
         self.initialize_lf_level(f_low, lf_X, lf_Y)
         self.add_noise = add_noise

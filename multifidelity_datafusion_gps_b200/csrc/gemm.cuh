@@ -149,22 +149,35 @@ struct GemmParams {
   double alpha, beta;
   int lower_only;                      // enumerate only tiles with ti >= tj (M == N)
   int kb_row, kb_col, ke_row;          // triangular operands: k >= row0 / k >= col0 / k < row0+BM
+  // batch of equally shaped, independent products along a diagonal (the nodes of one level of the
+  // triangular-inverse recursion): node b works on A + b*stride, B + b*stride, C + b*stride
+  int batch;                           // number of nodes (0 or 1: plain product)
+  long batch_stride;
 };
 
 template <class T, bool A_KC, bool B_KC>
 __global__ void __launch_bounds__(T::THREADS) gemm_kernel(GemmParams p) {
   extern __shared__ __align__(16) double smem[];
   int ti, tj;
+  int bid = blockIdx.x;
+  if (p.batch > 1) {
+    const int per_node = gridDim.x / p.batch;
+    const long off = (long)(bid / per_node) * p.batch_stride;
+    bid %= per_node;
+    p.A += off;
+    p.B += off;
+    p.C += off;
+  }
   if (p.lower_only) {
-    int tt = blockIdx.x;
+    int tt = bid;
     ti = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
     while ((long)(ti + 1) * (ti + 2) / 2 <= tt) ti++;
     while ((long)ti * (ti + 1) / 2 > tt) ti--;
     tj = tt - ti * (ti + 1) / 2;
   } else {
     const int tiles_n = p.N / T::BN;
-    ti = blockIdx.x / tiles_n;
-    tj = blockIdx.x % tiles_n;
+    ti = bid / tiles_n;
+    tj = bid % tiles_n;
   }
   const int row0 = ti * T::BM, col0 = tj * T::BN;
   int kb = 0, ke = p.K;

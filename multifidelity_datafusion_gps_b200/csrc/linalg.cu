@@ -22,18 +22,24 @@ constexpr int LEAF_LD = LEAF + 1;
 // (i = ty+16a, j = tx+16b).  Positions with j <= i hold A -> L; positions with j > i hold the
 // accumulators of W = L^-1 transposed (position (r,c), r < c, works on W[c][r]).  Per elimination
 // step only column k of that packed matrix goes through shared memory (double-buffered, one
-// __syncthreads per step); the rank-1 updates are pure register FMAs.
+// __syncthreads per step for factor AND inverse); the rank-1 updates are pure register FMAs.
 constexpr int LT = 16;   // thread grid edge; 8 = LEAF / LT elements per thread and dimension
 
+// One elimination step does both jobs with ONE barrier: column k of the packed matrix is published
+// whole -- rows >= k carry the (unscaled) column of L, rows < k the finished accumulators of W[k][.]
+// (contributions to W[k][r] come from steps < k only) -- then every thread applies the Cholesky
+// rank-1 update to its lower positions (i, j > k) and the inverse update
+//   acc(W[c][r]) += L[c][k] * W[k][r],  W[k][r] = -acc(k,r) / L[k][k]  (r < k),  W[k][k] = 1 / L[k][k]
+// to its upper positions (r <= k < c).  128 barriers per leaf instead of 256.
 template <int KB>
-__device__ __forceinline__ void leaf_chol_block(double (&t)[8][8], double (*col)[LEAF], double* dinv,
-                                                int tx, int ty, int* info, int j0) {
+__device__ __forceinline__ void leaf_fused_block(double (&t)[8][8], double (*col)[LEAF], double* dinv,
+                                                 int tx, int ty, int* info, int j0) {
   for (int ko = 0; ko < LT; ko++) {
     const int k = KB * LT + ko;
     double* buf = col[k & 1];
-    if (tx == ko) {   // owners of column k publish it (unscaled), rows >= k only matter
+    if (tx == ko) {   // owners of column k of the packed matrix
 #pragma unroll
-      for (int a = KB; a < 8; a++) buf[ty + LT * a] = t[a][KB];
+      for (int a = 0; a < 8; a++) buf[ty + LT * a] = t[a][KB];
     }
     __syncthreads();
     double p = buf[k];
@@ -42,7 +48,7 @@ __device__ __forceinline__ void leaf_chol_block(double (&t)[8][8], double (*col)
       p = 1.0;
     }
     const double rinv = rsqrt(p);
-    if (tx == ko) {   // owners keep the scaled column = column k of L
+    if (tx == ko) {   // owners keep the scaled column = column k of L (rows < k keep the W accumulators)
 #pragma unroll
       for (int a = KB; a < 8; a++) {
         const int i = ty + LT * a;
@@ -50,13 +56,18 @@ __device__ __forceinline__ void leaf_chol_block(double (&t)[8][8], double (*col)
         else if (i == k) { t[a][KB] = p * rinv; dinv[k] = rinv; }
       }
     }
-    double li[8], lj[8];
+    double li[8], lj[8], wr[8];
 #pragma unroll
-    for (int a = KB; a < 8; a++) li[a] = buf[ty + LT * a] * rinv;
+    for (int a = KB; a < 8; a++) li[a] = buf[ty + LT * a] * rinv;       // L[i][k], rows i > k
 #pragma unroll
-    for (int b = KB; b < 8; b++) lj[b] = buf[tx + LT * b] * rinv;
+    for (int b = KB; b < 8; b++) lj[b] = buf[tx + LT * b] * rinv;       // L[j][k], columns j > k
 #pragma unroll
-    for (int a = KB; a < 8; a++) {
+    for (int a = 0; a <= KB; a++) {                                     // W[k][r], rows r <= k
+      const int r = ty + LT * a;
+      wr[a] = (r == k) ? rinv : -rinv * buf[r];
+    }
+#pragma unroll
+    for (int a = KB; a < 8; a++) {                                      // Cholesky: lower positions
       if (a == KB && ty <= ko) continue;          // row i <= k
 #pragma unroll
       for (int b = KB; b <= a; b++) {
@@ -65,36 +76,13 @@ __device__ __forceinline__ void leaf_chol_block(double (&t)[8][8], double (*col)
         t[a][b] = fma(-li[a], lj[b], t[a][b]);
       }
     }
-  }
-}
-
-template <int KB>
-__device__ __forceinline__ void leaf_inv_block(double (&t)[8][8], double (*col)[LEAF], const double* dinv,
-                                               int tx, int ty) {
-  for (int ko = 0; ko < LT; ko++) {
-    const int k = KB * LT + ko;
-    double* buf = col[k & 1];
-    if (tx == ko) {   // column k of the packed matrix: r < k -> acc of W[k][r]; r > k -> L[r][k]
 #pragma unroll
-      for (int a = 0; a < 8; a++) buf[ty + LT * a] = t[a][KB];
-    }
-    __syncthreads();
-    const double dk = dinv[k];
-    double wr[8], lc[8];
-#pragma unroll
-    for (int a = 0; a <= KB; a++) {               // W[k][r] for this thread's rows r <= k
-      const int r = ty + LT * a;
-      wr[a] = (r == k) ? dk : -dk * buf[r];
-    }
-#pragma unroll
-    for (int b = KB; b < 8; b++) lc[b] = buf[tx + LT * b];   // L[c][k] for this thread's columns c > k
-#pragma unroll
-    for (int a = 0; a <= KB; a++) {
+    for (int a = 0; a <= KB; a++) {                                     // inverse: upper positions r <= k < c
       if (a == KB && ty > ko) continue;           // row r > k
 #pragma unroll
       for (int b = KB; b < 8; b++) {
         if (b == KB && tx <= ko) continue;        // column c <= k
-        t[a][b] = fma(lc[b], wr[a], t[a][b]);     // acc(W[c][r]) += L[c][k] * W[k][r]
+        t[a][b] = fma(lj[b], wr[a], t[a][b]);     // acc(W[c][r]) += L[c][k] * W[k][r]
       }
     }
   }
@@ -115,23 +103,15 @@ __global__ void __launch_bounds__(256, 1)
       const int i = ty + LT * a, j = tx + LT * b;
       t[a][b] = (j <= i) ? A[(long)i * lda + j] : 0.0;
     }
-  leaf_chol_block<0>(t, col, dinv, tx, ty, info, j0);
-  leaf_chol_block<1>(t, col, dinv, tx, ty, info, j0);
-  leaf_chol_block<2>(t, col, dinv, tx, ty, info, j0);
-  leaf_chol_block<3>(t, col, dinv, tx, ty, info, j0);
-  leaf_chol_block<4>(t, col, dinv, tx, ty, info, j0);
-  leaf_chol_block<5>(t, col, dinv, tx, ty, info, j0);
-  leaf_chol_block<6>(t, col, dinv, tx, ty, info, j0);
-  leaf_chol_block<7>(t, col, dinv, tx, ty, info, j0);
+  leaf_fused_block<0>(t, col, dinv, tx, ty, info, j0);
+  leaf_fused_block<1>(t, col, dinv, tx, ty, info, j0);
+  leaf_fused_block<2>(t, col, dinv, tx, ty, info, j0);
+  leaf_fused_block<3>(t, col, dinv, tx, ty, info, j0);
+  leaf_fused_block<4>(t, col, dinv, tx, ty, info, j0);
+  leaf_fused_block<5>(t, col, dinv, tx, ty, info, j0);
+  leaf_fused_block<6>(t, col, dinv, tx, ty, info, j0);
+  leaf_fused_block<7>(t, col, dinv, tx, ty, info, j0);
   __syncthreads();   // dinv complete; col buffers free
-  leaf_inv_block<0>(t, col, dinv, tx, ty);
-  leaf_inv_block<1>(t, col, dinv, tx, ty);
-  leaf_inv_block<2>(t, col, dinv, tx, ty);
-  leaf_inv_block<3>(t, col, dinv, tx, ty);
-  leaf_inv_block<4>(t, col, dinv, tx, ty);
-  leaf_inv_block<5>(t, col, dinv, tx, ty);
-  leaf_inv_block<6>(t, col, dinv, tx, ty);
-  leaf_inv_block<7>(t, col, dinv, tx, ty);
   // stage the packed matrix, then write L and W with coalesced rows
 #pragma unroll
   for (int a = 0; a < 8; a++)
@@ -169,7 +149,7 @@ int tile_variant() {
 template <class T>
 int tile_count(const dg::GemmParams& p) {
   const int tm = p.M / T::BM, tn = p.N / T::BN;
-  return p.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  return (p.lower_only ? tm * (tm + 1) / 2 : tm * tn) * (p.batch > 1 ? p.batch : 1);
 }
 
 // Narrow GEMMs (fewer 128x128 tiles than SMs) sit on the critical path of the recursion: run them
@@ -399,8 +379,43 @@ int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad) {
   return potrf_rec(h, A, W, npad, 0, npad);
 }
 
+// Level-synchronous form of trtri_rec for npad = 128 * 2^q: the nodes of one level are independent and
+// equally shaped, so each level is TWO launches over all of its nodes (14 launches at N = 16384
+// instead of 254); the deep levels, whose single nodes fill only a fraction of the SMs, then run as
+// one grid.
+static int trtri_levels(mfgp_ctx* h, const double* L, double* W, int npad) {
+  const long ld = npad;
+  int rc;
+  for (int n = 2 * LEAF; n <= npad; n *= 2) {
+    const int n1 = n / 2, nodes = npad / n;
+    const long stride = (long)n * (ld + 1);
+    const double* W11 = W;
+    const double* W22 = W + (long)n1 * ld + n1;
+    const double* L21 = L + (long)n1 * ld;
+    double* Tt = W + n1;                  // n1 x n1 scratch in W's (unused) upper block
+    double* W21 = W + (long)n1 * ld;
+    {  // Tt[c][r] = sum_{k>=c} W11[k][c] * L21[r][k]
+      dg::GemmParams p = gp(W11, ld, L21, ld, Tt, ld, n1, n1, n1, 1.0, 0.0);
+      p.kb_row = 1;
+      p.batch = nodes;
+      p.batch_stride = stride;
+      if ((rc = launch_gemm<false, true>(h, p))) return rc;
+    }
+    {  // W21[r][c] = -sum_{k<=r} W22[r][k] * Tt[c][k]
+      dg::GemmParams p = gp(W22, ld, Tt, ld, W21, ld, n1, n1, n1, -1.0, 0.0);
+      p.ke_row = 1;
+      p.batch = nodes;
+      p.batch_stride = stride;
+      if ((rc = launch_gemm<true, true>(h, p))) return rc;
+    }
+  }
+  return 0;
+}
+
 int trtri_padded(mfgp_ctx* h, const double* L, double* W, int npad) {
   ARG_CHECK(h, npad > 0 && npad % LEAF == 0);
+  const int m = npad / LEAF;
+  if ((m & (m - 1)) == 0) return trtri_levels(h, L, W, npad);
   return trtri_rec(h, L, W, npad, 0, npad);
 }
 

@@ -66,11 +66,13 @@ class OracleMFGP:
 
     def __init__(self, input_dim, num_derivatives, tau, f_exact, f_low=None, lf_X=None,
                  lf_Y=None, use_composite_kernel=True, add_noise=False, lower_bound=None,
-                 upper_bound=None, form="gpy", lf_theta=None, rng=None):
+                 upper_bound=None, form="gpy", lf_theta=None, rng=None, offsets=None):
         self.input_dim = input_dim
         self.tau = tau
         self.f_exact = f_exact
         self.offsets = backward_offsets(num_derivatives, input_dim)   # MFDataFusion.py:67
+        if offsets is not None:                                        # e.g. even_offsets(n, dim)
+            self.offsets = np.asarray(offsets, dtype=np.float64)
         self.kind = go.KIND_COMPOSITE if use_composite_kernel else go.KIND_RBF
         P = 7 if use_composite_kernel else 3
         self.theta = np.ones(P)            # kernel object persists across fits (:96 warm start)

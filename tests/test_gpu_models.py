@@ -405,3 +405,22 @@ def test_adaptation_with_bordered_updates_between_refits(pkg):
     assert util.rel_err(mean, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.2) < 1e-6
     m.adapt(3)                                                    # third step of this call refits
     assert m.hf_model.N == 10 and not np.array_equal(m.hf_model.param_array, theta0)
+
+
+def test_even_delay_pattern_is_selectable_and_matches_oracle(pkg):
+    # src/augm_iterators/even_augm_iterator.py: 2*n*dim + 1 symmetric delays (here n = 1, dim = 2 -> E = 5)
+    _, X_hf, X_test = _data(2)
+    X_hf = np.vstack([X_hf, np.random.RandomState(5).uniform(size=(20, 2))])
+    m = pkg.MultifidelityDataFusion("even", 2, 1, 0.01, util.hf_2d, f_low=util.lf_2d,
+                                    use_composite_kernel=False, augm_iterator="even")
+    assert isinstance(m.augm_iterator, pkg.EvenAugmentation) and m.augm_iterator.new_entries_count() == 5
+    m.fit(X_hf, theta=THETA_R)
+    o = mo.OracleMFGP(2, 1, 0.01, util.hf_2d, f_low=util.lf_2d, use_composite_kernel=False,
+                      offsets=mo.even_offsets(1, 2))
+    o.fit(X_hf, theta=THETA_R)
+    assert np.array_equal(m.hf_model.X, o.hf_model.X)
+    mean, var = m.predict(X_test)
+    mu_ref, var_ref = o.predict(X_test)
+    assert util.rel_err(mean, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.2) < 1e-6
+    # the presets keep the reference's default pattern
+    assert isinstance(pkg.GPDF(2, 0.01, 1, util.hf_2d, util.lf_2d).augm_iterator, pkg.BackwardAugmentation)
