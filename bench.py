@@ -391,7 +391,11 @@ def main():
         achieved = flops_per_launch / (trmm_ms * 1e-3) / 1e12 if trmm_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "dg::trmm_sumsq_kernel (tmp = W Kx, fused column sum of squares)",
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                    "frac": achieved / fp64_peak if fp64_peak else None,
+                    # DRAM read+write per launch from the ncu --set full capture of this kernel
+                    # (profiles/r01_ncu_mc_kernels_v3.txt: 1.616 GB for 75 776 columns at N_h = 1024),
+                    # scaled to this run's columns per launch
+                    "traffic": (1.616e9 / 75776.0 * cols_per_launch) if args.nh == 1024 else None,
                     "avg_launch_ms": trmm_ms, "launches_per_step": hf_launches_per_step,
                     "flops_per_launch": flops_per_launch,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no FP64 "
