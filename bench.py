@@ -419,6 +419,21 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": sample, "seconds": dt}
         if world == 1 and not args.no_lml:
+            # acquisition throughput (candidates/s for A9): arg-max of the predictive
+            # variance over the same M points taken as candidates, device-resident
+            acq_ms = []
+            for i in range(3):
+                s_a, e_a = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_a.record()
+                _, var_c = model._predict_device(dX)
+                c_val, c_idx = ops.argmax(var_c)
+                e_a.record(); torch.cuda.synchronize()
+                if i > 0:
+                    acq_ms.append(s_a.elapsed_time(e_a))
+            line["acquisition"] = {"candidates": int(M), "N_h": args.nh, "N_l": args.nl,
+                                   "ms": float(np.mean(acq_ms)),
+                                   "candidates_per_s": float(M / (np.mean(acq_ms) * 1e-3)),
+                                   "argmax_index": int(c_idx), "max_variance": float(c_val)}
             del dX
             gp._ws_pool.clear()
             torch.cuda.empty_cache()
