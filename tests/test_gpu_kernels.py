@@ -291,3 +291,45 @@ def test_bordered_update_matches_refactorisation(T, kind, d, E, N0):
     mu, var = m.predict(Xq)
     mu_ref, var_ref = ref.predict(Xq)
     assert util.rel_err(mu, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.5) < 1e-6
+
+
+def test_full_size_lml_grad_properties_n16384(T):
+    """BASELINE.json configs[3] at full size (N_h = 16384, look-ahead Cholesky, level-batched inverse):
+    properties that do not need the O(N^3) oracle -- K^-1 K_y = I and L L^T = K_y on sampled columns,
+    alpha solves the system, analytic gradient against central differences of the GPU LML."""
+    kind, d, E, N = go.KIND_COMPOSITE, 4, 1, 16384
+    torch = T.torch
+    rng = np.random.default_rng(1)
+    X4 = rng.uniform(size=(N, 4))
+    X = np.concatenate([X4, util.lf_4d(X4)], axis=1)
+    Y = util.hf_4d(X4)
+    th = np.array([1.0, 0.3, 1.0, 0.3, 0.1, 0.3, 0.01 * Y.var()])
+    dX, dy = T.up(X), T.up(Y.ravel())
+    buf = T.ops.FactorBuffers(N, T.dev)
+    lml, logdet, yta, info = T.ops.factorize(dX, dy, kind, d, th, buf)
+    assert info == 0 and np.isfinite(lml)
+    cols = torch.arange(5, N, 1021, device=T.dev)
+    Ky_cols = T.ops.assemble(dX, kind, d, th, uplo=1)[:, cols]          # (N, 17) of the full matrix
+    L = torch.tril(buf.A)
+    assert ((L @ L[cols, :].T) - Ky_cols).abs().max().item() < 1e-10
+    W = torch.tril(buf.W)
+    E_cols = torch.zeros((N, cols.numel()), dtype=torch.float64, device=T.dev)
+    E_cols[cols, torch.arange(cols.numel(), device=T.dev)] = 1.0
+    assert (W @ L[:, cols] - E_cols).abs().max().item() < 1e-9           # W L = I
+    del L, W
+    alpha = buf.alpha[:N].clone()
+    lml2, g, info = T.ops.lml_grad(dX, dy, kind, d, th, buf)
+    assert info == 0 and abs(lml2 - lml) <= 1e-12 * abs(lml)
+    Ki = torch.tril(buf.A) + torch.tril(buf.A, -1).T
+    assert (Ki @ Ky_cols - E_cols).abs().max().item() < 1e-6             # K^-1 K_y = I
+    assert (Ki @ dy - alpha).abs().max().item() < 1e-7 * alpha.abs().max().item()
+    del Ki
+    for i in (1, 6):
+        hstep = 1e-5 * th[i]
+        tp, tm = th.copy(), th.copy()
+        tp[i] += hstep
+        tm[i] -= hstep
+        lp = T.ops.factorize(dX, dy, kind, d, tp, buf)[0]
+        lm = T.ops.factorize(dX, dy, kind, d, tm, buf)[0]
+        fd = (lp - lm) / (2 * hstep)
+        assert abs(g[i] - fd) <= 2e-5 * max(1.0, abs(fd))

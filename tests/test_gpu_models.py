@@ -424,3 +424,43 @@ def test_even_delay_pattern_is_selectable_and_matches_oracle(pkg):
     assert util.rel_err(mean, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.2) < 1e-6
     # the presets keep the reference's default pattern
     assert isinstance(pkg.GPDF(2, 0.01, 1, util.hf_2d, util.lf_2d).augm_iterator, pkg.BackwardAugmentation)
+
+
+def test_full_size_mc_sweep_properties(pkg):
+    """BASELINE.json configs[4] at full size: M = 32^4 Gauss-Legendre nodes x S = 100 samples, N_h = 1024,
+    N_l = 4096.  The oracle covers a 256-point subsample; the full sweep is pinned by invariances: the
+    two halves evaluated separately (m0 = M/2, as two ranks would) and a different scratch size give the
+    same bits, and the fused PCE mean equals sum w * mean."""
+    import torch
+    from multifidelity_datafusion_gps_b200 import gp
+    rng = np.random.default_rng(1)
+    Xh, Xl = rng.uniform(size=(1024, 4)), rng.uniform(size=(4096, 4))
+    yh, yl = util.hf_4d(Xh), util.lf_4d(Xl)
+    lf_theta = np.array([1.0, 0.3, 0.01 * yl.var()])
+    hf_theta = np.array([1.0, 0.3, 1.0, 0.3, 0.1, 0.3, 0.01 * yh.var()])
+    m = pkg.NARGP(4, util.hf_4d, None, lf_X=Xl[:8], lf_Y=yl[:8])
+    m.lf_X, m.lf_Y = Xl, yl
+    m.lf_model = gp.GPRegression(Xl, yl)
+    m.lf_model._set_params(lf_theta)
+    m.fit(Xh, theta=hf_theta)
+    nodes, w = mo.gauss_legendre_grid(31, 4)                      # 32 nodes per dimension
+    M, S, seed = nodes.shape[0], 100, 2
+    assert M == 32 ** 4
+    dX, dw = gp.to_device(nodes, 0), gp.to_device(w, 0)
+    mean, var, wsum = m.predict_mc_device(dX, S, None, seed, 0, dw)
+    assert torch.isfinite(mean).all() and torch.isfinite(var).all() and (var > 0).all()
+    assert np.isclose(wsum, float((dw * mean).sum().item()), rtol=1e-12)
+    half = M // 2
+    mean_b, var_b, _ = m.predict_mc_device(dX[half:], S, None, seed, half)          # second half alone
+    assert torch.equal(mean_b, mean[half:]) and torch.equal(var_b, var[half:])
+    mean_c, var_c, _ = m.predict_mc_device(dX[:65536], S, None, seed, 0, ws_bytes=200 << 20)   # other chunking
+    assert torch.equal(mean_c, mean[:65536]) and torch.equal(var_c, var[:65536])
+    # oracle on a subsample, with the normals the in-kernel generator used for those points
+    from multifidelity_datafusion_gps_b200 import ops
+    o = mo.OracleMFGP(4, 0, 0, util.hf_4d, lf_X=Xl, lf_Y=yl, lf_theta=lf_theta)
+    o.fit(Xh, theta=hf_theta)
+    first, n = 777216, 256
+    eps = ops.fill_normal(seed, first * S, n * S, "cuda:0").cpu().numpy().reshape(n, S, 1)
+    mu_ref, var_ref = o.predict_mc(nodes[first:first + n], eps)
+    assert util.rel_err(mean[first:first + n].cpu().numpy()[:, None], mu_ref) < 1e-8
+    assert util.rel_err(var[first:first + n].cpu().numpy()[:, None], var_ref, 1.1) < 1e-6
