@@ -464,3 +464,35 @@ def test_full_size_mc_sweep_properties(pkg):
     mu_ref, var_ref = o.predict_mc(nodes[first:first + n], eps)
     assert util.rel_err(mean[first:first + n].cpu().numpy()[:, None], mu_ref) < 1e-8
     assert util.rel_err(var[first:first + n].cpu().numpy()[:, None], var_ref, 1.1) < 1e-6
+
+
+# ---- CUDA classes against what the reference's own code computed (tests/golden/reference_runs.npz) ----
+_REF_SCENARIOS = {
+    "nargp_1d": ("NARGP", dict(dim=1, hf=util.f_high_1d, lf=util.f_low_1d)),
+    "gpdf_2d": ("GPDF", dict(dim=2, hf=util.hf_2d, lf=util.lf_2d)),
+    "gpdfc_2d": ("GPDFC", dict(dim=2, hf=util.hf_2d, lf=util.lf_2d)),
+    "gpdf_2d_add_noise": ("GPDF", dict(dim=2, hf=util.hf_2d, lf=util.lf_2d, add_noise=True)),
+    "nargp_2d_adapt": ("NARGP", dict(dim=2, hf=util.hf_2d, lf=util.lf_2d)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_REF_SCENARIOS))
+def test_cuda_classes_match_the_executed_reference_at_fixed_theta(pkg, name):
+    """The golden file holds predictions of the REFERENCE's classes (src/ executed unmodified over the
+    oracle's GP arithmetic) on the training set its own fit / adaptation loop ended with, at fixed
+    hyper-parameters.  Same classes, same calls here, on the GPU: augmentation, add_noise and predict."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_runs.npz"))
+    cls, sc = _REF_SCENARIOS[name]
+    if cls == "NARGP":
+        m = pkg.NARGP(sc["dim"], sc["hf"], sc["lf"], add_noise=sc.get("add_noise", False))
+    else:
+        m = getattr(pkg, cls)(sc["dim"], 0.001, 2, sc["hf"], sc["lf"], add_noise=sc.get("add_noise", False))
+    m.fit(g[name + "/hf_X_final"], theta=g[name + "/theta_fixed"])
+    assert np.array_equal(m.hf_model.X, g[name + "/aug_X"])              # the reference's augmentation
+    assert np.array_equal(m.hf_Y, g[name + "/hf_Y_final"])
+    mean, var = m.predict(g[name + "/X_test"])
+    assert util.rel_err(mean, g[name + "/mean_fixed"]) < 1e-8
+    assert util.rel_err(var, g[name + "/var_fixed"], 1.2) < 1e-6
+    if not sc.get("add_noise"):
+        assert np.isclose(m.hf_model.log_likelihood(), float(g[name + "/lml_fixed"]), rtol=1e-6)
