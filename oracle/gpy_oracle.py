@@ -14,7 +14,8 @@ golden vectors for this boundary.  This file therefore re
 GPy's *published algorithm* from memory of the upstream sources named below; it is
 validated by finite differences, closed-form 1-/2-point GP cases and a second,
 independently written direct-solve formulation (``tests/test_oracle.py``), not by the
-reference's own outputs.
+reference's own outputs.  (What the reference itself owns -- the orchestration around this
+engine -- IS pinned by executing its code over this module: see ``oracle/mfgp_oracle.py``.)
 
 Upstream files followed, by name (GPy 1.9.9):
   GPy/kern/src/stationary.py   Stationary._unscaled_dist / _scaled_dist / K /

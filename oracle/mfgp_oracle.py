@@ -1,8 +1,11 @@
 """CPU oracle for the reference's own orchestration on the hot path.
 
-TEST INFRASTRUCTURE ONLY -- see the header of ``oracle/gpy_oracle.py`` (parity unpinned:
-the GP arithmetic is a restatement of GPy 1.9.9, which cannot be run here).  The parts
-below follow the *reference's* code, which is present and cited line by line:
+TEST INFRASTRUCTURE ONLY -- see the header of ``oracle/gpy_oracle.py`` (the GP arithmetic
+underneath is a restatement of GPy 1.9.9, which cannot be run here: that part is unpinned).
+THIS module's part IS pinned: tests/golden/reference_runs.npz holds what the reference's own
+classes compute when /root/reference/src is executed unmodified over the same GP arithmetic
+(tests/golden/make_reference_run_golden.py), and tests/test_oracle.py requires this restatement
+to reproduce those runs.  The parts below follow the *reference's* code, cited line by line:
 
   A1  delay augmentation        src/MFDataFusion.py:177-208,
                                 src/augm_iterators/backward_augm_iterator.py:20-37,
