@@ -203,9 +203,10 @@ __global__ void __launch_bounds__(256)
                         const double* __restrict__ mu_l, const double* __restrict__ sd_l,
                         const double* __restrict__ eps, unsigned long long seed, long long m_global0,
                         long long m_lo, int S, double* __restrict__ Ks, double* __restrict__ mu_c) {
-  extern __shared__ __align__(16) double stbl_all[];   // exp table (dynamic: 32 KB)
+  extern __shared__ __align__(16) double stbl_all[];   // exp table (32 KB) | zs[MC_MAXS]
   __shared__ __align__(16) double su[MC_KCHUNK], sv[MC_KCHUNK], sz[MC_KCHUNK], sa[MC_KCHUNK];
   __shared__ double macc[MC_MAXS];
+  double* zs = stbl_all + fm::EXP_TBL_DOUBLES;
   fm::load_exp_table(stbl_all, kp.exp_tbl);
   const unsigned tbl = fm::lane_table(stbl_all);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -215,7 +216,13 @@ __global__ void __launch_bounds__(256)
   for (int dd = 0; dd < d; dd++) xm[dd] = Xtest[m * d + dd];
   const double mul = mu_l[m], sdl = sd_l[m];
   const double uz = kp.uz;
-  for (int s = tid; s < S; s += 256) macc[s] = 0.0;
+  // all S low-fidelity samples of this point up front, one thread each (Philox + Box-Muller costs a few
+  // hundred instructions: left to lane 0 of the sample's warp it stalled the other 31 lanes)
+  for (int s = tid; s < S; s += 256) {
+    macc[s] = 0.0;
+    const double e = eps ? eps[m * S + s] : philox_normal((unsigned long long)((m_global0 + m) * S + s), seed);
+    zs[s] = fma(sdl, e, mul);
+  }
   for (int k0 = 0; k0 < npad; k0 += MC_KCHUNK) {
     const int klen = min(MC_KCHUNK, npad - k0);
     __syncthreads();
@@ -241,11 +248,7 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     for (int s = warp; s < S; s += 8) {
-      double e = 0.0;
-      if (lane == 0)
-        e = eps ? eps[m * S + s] : philox_normal((unsigned long long)((m_global0 + m) * S + s), seed);
-      e = __shfl_sync(0xffffffffu, e, 0);
-      const double z = fma(sdl, e, mul);
+      const double z = zs[s];
       double* row = Ks + ((long long)blockIdx.x * S + s) * npad + k0;
       double acc = 0.0;
       const int kval = min(klen, N - k0);        // training points in this chunk (the rest is pad)
@@ -698,7 +701,7 @@ int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, 
   if (npts <= 0) return 0;
   ARG_CHECK(h, S <= MC_MAXS);
   prof_begin(h, PC_CROSSGEN);
-  cross_gen_mc_kernel<<<(unsigned)npts, 256, fm::EXP_TBL_BYTES, h->stream>>>(
+  cross_gen_mc_kernel<<<(unsigned)npts, 256, fm::EXP_TBL_BYTES + MC_MAXS * sizeof(double), h->stream>>>(
       kp, X, N, npad, alpha, Xtest, mu_l, sd_l, eps, seed, m_global0, m_lo, S, Ks, mu_c);
   prof_end(h, PC_CROSSGEN);
   LAUNCH_CHECK(h);
@@ -714,7 +717,7 @@ int mc_max_samples() { return MC_MAXS; }
 
 int predict_configure(mfgp_ctx* h) {
   CUDA_TRY(h, cudaFuncSetAttribute(cross_gen_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fm::EXP_TBL_BYTES));
+                                   fm::EXP_TBL_BYTES + MC_MAXS * (int)sizeof(double)));
   return 0;
 }
 
