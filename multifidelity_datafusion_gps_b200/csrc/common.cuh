@@ -117,5 +117,7 @@ int trmm_store(mfgp_ctx* h, const double* W, int npad, const double* Ks, long lo
 int assemble_configure(mfgp_ctx* h);
 int assemble_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, double diag_add,
                     double* K, long long ldk, int uplo, int npad_identity);
+int cross_tile_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int npad, const double* alpha,
+                      const double* Xq, long long ncols, long long cols_pad, double* Ks, double* mean);
 int grad_reduce_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, const double* Kinv,
                        long long ld, const double* alpha, double* d_out8);

@@ -674,6 +674,11 @@ int cross_gen_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int
   if (cols_pad <= 0) return 0;
   const unsigned grid = nblk(cols_pad, 8);
   prof_begin(h, PC_CROSSGEN);
+  if (cross_tile_launch(h, kp, X, N, npad, alpha, Xq, ncols, cols_pad, Ks, mean)) {   // large batches: tiled kernel
+    prof_end(h, PC_CROSSGEN);
+    LAUNCH_CHECK(h);
+    return 0;
+  }
 #define MFGP_XGEN(DT)                                                                              \
   case DT:                                                                                         \
     cross_gen_fixed_kernel<DT><<<grid, 256, 0, h->stream>>>(kp, X, N, npad, alpha, Xq, ncols,      \
