@@ -54,9 +54,11 @@ def test_public_surface_matches_reference_signatures():
     import multifidelity_datafusion_gps_b200 as pkg
     sig = lambda f: list(inspect.signature(f).parameters)
     # src/MFDataFusion.py:56-59
-    assert sig(pkg.MultifidelityDataFusion.__init__)[1:] == [
-        "name", "input_dim", "num_derivatives", "tau", "f_exact", "lower_bound", "upper_bound", "f_low",
-        "lf_X", "lf_Y", "lf_hf_adapt_ratio", "use_composite_kernel", "adapt_maximizer", "eps", "add_noise"]
+    ref = ["name", "input_dim", "num_derivatives", "tau", "f_exact", "lower_bound", "upper_bound", "f_low",
+           "lf_X", "lf_Y", "lf_hf_adapt_ratio", "use_composite_kernel", "adapt_maximizer", "eps", "add_noise"]
+    ours = sig(pkg.MultifidelityDataFusion.__init__)[1:]
+    assert ours[:len(ref)] == ref                      # the reference's parameters, same order
+    assert ours[len(ref):] == ["augm_iterator"]        # extensions come after them, keyword-style
     # src/models/NARGP.py:15-17
     assert sig(pkg.NARGP.__init__)[1:12] == ["input_dim", "f_exact", "f_low", "name", "lower_bound",
                                              "upper_bound", "lf_X", "lf_Y", "lf_hf_adapt_ratio", "eps", "add_noise"]
