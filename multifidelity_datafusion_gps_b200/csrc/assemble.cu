@@ -625,7 +625,11 @@ int grad_reduce_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, c
 int cross_tile_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int npad, const double* alpha,
                       const double* Xq, long long ncols, long long cols_pad, double* Ks, double* mean) {
   const Shape sh = shape_of(kp);
-  if (sh.DT == 0 || ncols < 16 * BT || (Ks && cols_pad % BT != 0)) return 0;
+  if (sh.DT == 0 || (Ks && cols_pad % BT != 0)) return 0;
+  // The two generators produce bit-identical ELEMENTS but reduce the mean in different orders, so which
+  // one computes a mean must not depend on the batch size (predictions are bit-invariant to chunking
+  // and sharding): with a mean this kernel always runs; small element-only batches take the light one.
+  if (!mean && ncols < 16 * BT) return 0;
   // with an output block the pad rows up to cols_pad are zero-filled; mean-only needs the real rows only
   const unsigned grid = (unsigned)(Ks ? cols_pad / BT : (ncols + BT - 1) / BT);
   bool done = false;

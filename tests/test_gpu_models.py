@@ -496,3 +496,17 @@ def test_cuda_classes_match_the_executed_reference_at_fixed_theta(pkg, name):
     assert util.rel_err(var, g[name + "/var_fixed"], 1.2) < 1e-6
     if not sc.get("add_noise"):
         assert np.isclose(m.hf_model.log_likelihood(), float(g[name + "/lml_fixed"]), rtol=1e-6)
+
+
+def test_predictions_are_bit_invariant_to_batch_size(pkg):
+    """A shard of the test points must give the bits the full batch gives for those points, whatever the
+    shard size (kernel selection must not depend on it): 4000 points against shards of 37, 1000, 2500."""
+    m, _ = _mc_models(pkg)
+    Xt = np.random.default_rng(21).uniform(size=(4000, 4))
+    mean, var = m.predict(Xt)
+    mc_mean, mc_var = m.predict_mc(Xt, n_samples=8, seed=4)
+    for lo, hi in ((0, 37), (1000, 2000), (1500, 4000)):
+        mu_s, var_s = m.predict(Xt[lo:hi])
+        assert np.array_equal(mu_s, mean[lo:hi]) and np.array_equal(var_s, var[lo:hi])
+        mc_mu_s, mc_var_s = m.predict_mc(Xt[lo:hi], n_samples=8, seed=4, m0=lo)
+        assert np.array_equal(mc_mu_s, mc_mean[lo:hi]) and np.array_equal(mc_var_s, mc_var[lo:hi])
