@@ -409,14 +409,16 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
 
 // ---- dispatch on (input width, trailing z columns) -----------------------------------------------
 // RBF kind: az == ax, so every column is treated as an x column (E = 0).  Composite: E = D - d.
-// Specialised for D <= 8 with E in {0, 1} (plain GP levels, NARGP, GPDF); everything else (GPDFC with
-// delays: composite with E > 1; D > 8) takes the runtime-width kernel.
+// Specialised for D <= 8 with E in {0, 1} (plain GP levels, NARGP, GPDF) and for the composite kernel
+// with two backward delays in 1-D and 2-D (GPDFC: d = 1, E = 3 and d = 2, E = 5, tests/test_mfgp_adapt_2d.py:27);
+// everything else (D > 8, other composite splits) takes the runtime-width kernel.
 struct Shape {
   int DT, E;
 };
 Shape shape_of(const KParams& kp) {
   const int E = kp.kind == MFGP_KIND_RBF ? 0 : kp.D - kp.d;
   if (kp.D <= MAX_DT && E <= 1) return {kp.D, E};
+  if ((kp.D == 4 && E == 3) || (kp.D == 7 && E == 5)) return {kp.D, E};
   return {0, 0};
 }
 
@@ -539,7 +541,7 @@ constexpr size_t grad_smem(int D) { return fm::EXP_TBL_BYTES + (size_t)2 * 2 * (
 
 #define MFGP_SHAPES(M)                                                                       \
   M(1, 0) M(2, 0) M(3, 0) M(4, 0) M(5, 0) M(6, 0) M(7, 0) M(8, 0)                            \
-  M(2, 1) M(3, 1) M(4, 1) M(5, 1) M(6, 1) M(7, 1) M(8, 1)
+  M(2, 1) M(3, 1) M(4, 1) M(5, 1) M(6, 1) M(7, 1) M(8, 1) M(4, 3) M(7, 5)
 
 }  // namespace
 

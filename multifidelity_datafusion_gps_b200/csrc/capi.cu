@@ -145,7 +145,6 @@ int mfgp_create(int device, mfgp_handle_t* out) {
             cudaMalloc(&h->d_scalars, MFGP_SMALL * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&h->d_info, 4 * sizeof(int)) == cudaSuccess &&
             cudaMalloc(&h->d_exp_tbl, 256 * sizeof(double)) == cudaSuccess &&
-            cudaMalloc(&h->d_counters, 16 * sizeof(int)) == cudaSuccess &&
             cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) == cudaSuccess &&
             cudaMallocHost(&h->h_info, 4 * sizeof(int)) == cudaSuccess;
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
@@ -156,8 +155,7 @@ int mfgp_create(int device, mfgp_handle_t* out) {
     ok = cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest) == cudaSuccess &&
          cudaStreamCreateWithPriority(&h->s_hi, cudaStreamNonBlocking, pr_greatest) == cudaSuccess;
   }
-  if (ok) ok = cudaMemset(h->d_info, 0, 4 * sizeof(int)) == cudaSuccess &&
-               cudaMemset(h->d_counters, 0, 16 * sizeof(int)) == cudaSuccess;
+  if (ok) ok = cudaMemset(h->d_info, 0, 4 * sizeof(int)) == cudaSuccess;
   if (ok) {   // 2^(j/256) rounded from 64-bit-mantissa long double
     double tbl[256];
     for (int j = 0; j < 256; j++) tbl[j] = (double)exp2l((long double)j / 256.0L);
@@ -180,7 +178,6 @@ int mfgp_destroy(mfgp_handle_t h) {
   cudaFree(h->d_scalars);
   cudaFree(h->d_info);
   cudaFree(h->d_exp_tbl);
-  cudaFree(h->d_counters);
   cudaFreeHost(h->h_pinned);
   cudaFreeHost(h->h_info);
   for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);

@@ -38,7 +38,6 @@ struct mfgp_ctx {
   double* d_scalars;      // 64 doubles: results staged for the host
   int* d_info;            // 4 ints: [0] first bad pivot (1-based, 0 = ok)
   double* d_exp_tbl;      // 256 doubles: 2^(j/256), correctly rounded on the host
-  int* d_counters;        // 16 ints: dynamic tile counters (zeroed before use)
   double* h_pinned;       // 64 doubles pinned
   int* h_info;            // 4 ints pinned
   cudaEvent_t ev[8];
