@@ -27,8 +27,10 @@ def T(gpu):
     return ns
 
 
+# (kind, d, E): the shapes with compile-time kernels (NARGP 1-D / 4-D, GPDFC and GPDF 2-D with delays, a
+# plain 3-D level) and two that take the runtime-width kernels (composite with E = 2; D = 11 > 8)
 CASES = [(go.KIND_COMPOSITE, 1, 1), (go.KIND_COMPOSITE, 2, 5), (go.KIND_COMPOSITE, 4, 1),
-         (go.KIND_RBF, 2, 5), (go.KIND_RBF, 3, 0)]
+         (go.KIND_RBF, 2, 5), (go.KIND_RBF, 3, 0), (go.KIND_COMPOSITE, 3, 2), (go.KIND_RBF, 2, 9)]
 
 
 @pytest.mark.parametrize("kind,d,E", CASES)
