@@ -32,6 +32,28 @@ __device__ __forceinline__ double exp_var(double u, unsigned tbl) {
   return __hiloint2double(hi, __double2loint(res));
 }
 
+// V 5: rounding on the XU pipe (FRND.F64 + F2I.S32.F64 saturating) instead of the magic-number DADDs
+template <>
+__device__ __forceinline__ double exp_var<5>(double u, unsigned tbl) {
+  double r;
+  int n;
+  asm("cvt.rni.f64.f64 %0, %1;" : "=d"(r) : "d"(u));
+  asm("cvt.rni.s32.f64 %0, %1;" : "=r"(n) : "d"(u));
+  n = max(n, -261632);
+  const double f = u - r;
+  double h = fma(f, 2.239395190875157e-12, 3.3083026805413713e-09);
+  h = fma(h, f, 3.6655655969101062e-06);
+  h = fma(h, f, 2.7076061740622863e-03);
+  double T;
+  asm("{\n\t.reg .u32 j, a;\n\tand.b32 j, %1, 255;\n\tmad.lo.u32 a, j, 128, %2;\n\tld.shared.f64 %0, [a];\n\t}"
+      : "=d"(T) : "r"(n), "r"(tbl));
+  const double res = fma(T, h * f, T);
+  int hi;
+  asm("{\n\t.reg .u32 q;\n\tand.b32 q, %1, 0xffffff00;\n\tmad.lo.u32 %0, q, 4096, %2;\n\t}"
+      : "=r"(hi) : "r"(n), "r"(__double2hiint(res)));
+  return __hiloint2double(hi, __double2loint(res));
+}
+
 template <int V, int NCH>
 __global__ void __launch_bounds__(1024) probe(int iters, double* out, double scale) {
   extern __shared__ double stbl[];
@@ -74,6 +96,7 @@ void run(double* d, int threads) {
 int main() {
   double* d;
   cudaMalloc(&d, 8);
+  run<5, 8>(d, 512); run<5, 16>(d, 512); run<5, 8>(d, 1024);
   run<0, 8>(d, 512); run<1, 8>(d, 512); run<2, 8>(d, 512); run<3, 8>(d, 512); run<4, 8>(d, 512);
   run<0, 16>(d, 512); run<0, 8>(d, 1024); run<0, 4>(d, 1024); run<4, 16>(d, 512);
   printf("%s\n", cudaGetErrorString(cudaGetLastError()));
