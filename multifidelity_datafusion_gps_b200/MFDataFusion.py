@@ -157,6 +157,14 @@ class MultifidelityDataFusion(AbstractMFGP):
                                        offs.ctypes.data_as(ctypes.c_void_p), E, float(self.tau),
                                        out.data_ptr(), ws.data_ptr(), ws.numel() * 8))
             return out
+        dev_f = getattr(self.f_low, "device_predict", None)
+        if dev_f is not None:
+            # a callable low fidelity that can evaluate on the device (e.g. the mean of another model of this
+            # package, models.MultiLevelNARGP): locations and augmented rows never leave the GPU
+            offs = torch.from_numpy(np.ascontiguousarray(offsets * self.tau, dtype=np.float64)).to(dX.device)
+            loc = (dX[:, None, :] + offs[None, :, :]).reshape(M * E, self.input_dim).contiguous()
+            vals = dev_f(loc).reshape(M, E)
+            return torch.cat([dX, vals], dim=1).contiguous()
         X = dX.cpu().numpy()
         locations = X[:, None, :] + offsets[None, :, :] * self.tau
         Xa = np.concatenate([X, self._f_low_batched(locations)], axis=1)

@@ -510,3 +510,25 @@ def test_predictions_are_bit_invariant_to_batch_size(pkg):
         assert np.array_equal(mu_s, mean[lo:hi]) and np.array_equal(var_s, var[lo:hi])
         mc_mu_s, mc_var_s = m.predict_mc(Xt[lo:hi], n_samples=8, seed=4, m0=lo)
         assert np.array_equal(mc_mu_s, mc_mean[lo:hi]) and np.array_equal(mc_var_s, mc_var[lo:hi])
+
+
+def test_three_level_nargp_recursion_matches_oracle_chain(pkg):
+    # level 1 GP -> level 2 NARGP on [x, mu_1(x)] -> level 3 NARGP on [x, mu_2(x)]
+    from multifidelity_datafusion_gps_b200.models import MultiLevelNARGP
+    rs = np.random.RandomState(13)
+    X1, X2, X3 = rs.uniform(size=(80, 2)), rs.uniform(size=(30, 2)), rs.uniform(size=(12, 2))
+    f1 = lambda x: util.lf_2d(x) + 0.3 * np.cos(4 * x[:, :1])
+    Y1, Y2, Y3 = f1(X1), util.lf_2d(X2), util.hf_2d(X3)
+    lf_theta = np.array([1.5, 0.4, 1e-3])
+    ml = MultiLevelNARGP(2, [X1, X2, X3], [Y1, Y2, Y3]).fit(thetas=[THETA_C, THETA_C], lf_theta=lf_theta)
+    o2 = mo.OracleMFGP(2, 0, 0, lambda X: Y2, lf_X=X1, lf_Y=Y1, lf_theta=lf_theta)
+    o2.fit(X2, theta=THETA_C)
+    o3 = mo.OracleMFGP(2, 0, 0, lambda X: Y3, f_low=lambda x: o2.predict(x)[0])
+    o3.fit(X3, theta=THETA_C)
+    Xt = rs.uniform(size=(500, 2))
+    mean, var = ml.predict(Xt)
+    mu_ref, var_ref = o3.predict(Xt)
+    assert util.rel_err(ml.models[-1].hf_model.X, o3.hf_model.X) < 1e-8     # augmentation through level 2
+    assert util.rel_err(mean, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.2) < 1e-6
+    mean2, _ = ml.predict_level(2, Xt)
+    assert util.rel_err(mean2, o2.predict(Xt)[0]) < 1e-8
