@@ -287,32 +287,48 @@ __global__ void __launch_bounds__(256)
 
 
 // ---- K7 with delays: joint low-fidelity posterior at the E augmented locations of a test point ----
-// G[p][a,b] = sum_i T[i][p*E+a] * T[i][p*E+b]  (packed lower triangle, a >= b); one thread per point,
-// rows of T are read coalesced (adjacent points are adjacent columns), fixed summation order.
+// G[p][a,b] = sum_i T[i][p*E+a] * T[i][p*E+b]  (packed lower triangle, a >= b); eight threads per point
+// (row groups), rows of T read coalesced (adjacent points are adjacent columns), fixed summation order.
+constexpr int GG_PTS = 16, GG_RG = 8;   // points per CTA x row groups: 128 threads
 template <int E>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(GG_PTS * GG_RG)
     group_gram_kernel(const double* __restrict__ T, int npad, long long ldt, long long npts,
                       double* __restrict__ G) {
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= npts) return;
+  // thread (rg, pl): point p = 16*blockIdx + pl, rows i = rg, rg+8, ...; threads of one row group read
+  // adjacent columns (coalesced); the 8 partial Grams of a point are added in row-group order
   constexpr int NP = E * (E + 1) / 2;
+  __shared__ double part[GG_RG][GG_PTS][NP];
+  const int pl = threadIdx.x % GG_PTS, rg = threadIdx.x / GG_PTS;
+  const long long p = (long long)blockIdx.x * GG_PTS + pl;
   double acc[NP];
 #pragma unroll
   for (int q = 0; q < NP; q++) acc[q] = 0.0;
-  const double* col = T + p * E;
+  if (p < npts) {
+    const double* col = T + p * E;
 #pragma unroll 4
-  for (int i = 0; i < npad; i++) {
-    double v[E];
+    for (int i = rg; i < npad; i += GG_RG) {
+      double v[E];
 #pragma unroll
-    for (int e = 0; e < E; e++) v[e] = col[(long long)i * ldt + e];
-    int q = 0;
+      for (int e = 0; e < E; e++) v[e] = col[(long long)i * ldt + e];
+      int q = 0;
 #pragma unroll
-    for (int a = 0; a < E; a++)
+      for (int a = 0; a < E; a++)
 #pragma unroll
-      for (int b = 0; b <= a; b++, q++) acc[q] = fma(v[a], v[b], acc[q]);
+        for (int b = 0; b <= a; b++, q++) acc[q] = fma(v[a], v[b], acc[q]);
+    }
   }
 #pragma unroll
-  for (int q = 0; q < NP; q++) G[p * NP + q] = acc[q];
+  for (int q = 0; q < NP; q++) part[rg][pl][q] = acc[q];
+  __syncthreads();
+  if (rg == 0 && p < npts) {
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+      double v = part[0][pl][q];
+#pragma unroll
+      for (int r = 1; r < GG_RG; r++) v += part[r][pl][q];
+      G[p * NP + q] = v;
+    }
+  }
 }
 
 // cov = kab - G (diagonal clipped at 1e-15 like GPy's predictive variance, then + diag_add);
@@ -775,7 +791,7 @@ int group_gram_launch(mfgp_ctx* h, const double* T, int npad, long long ldt, lon
   if (npts <= 0) return 0;
 #define MFGP_GG(E_)                                                                          \
   case E_:                                                                                   \
-    group_gram_kernel<E_><<<nblk(npts, 128), 128, 0, h->stream>>>(T, npad, ldt, npts, G);   \
+    group_gram_kernel<E_><<<nblk(npts, GG_PTS), GG_PTS * GG_RG, 0, h->stream>>>(T, npad, ldt, npts, G); \
     break;
   switch (E) {
     MFGP_GG(1) MFGP_GG(2) MFGP_GG(3) MFGP_GG(4) MFGP_GG(5) MFGP_GG(6) MFGP_GG(7) MFGP_GG(8)
