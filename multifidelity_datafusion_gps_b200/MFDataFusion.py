@@ -220,10 +220,13 @@ class MultifidelityDataFusion(AbstractMFGP):
         assert E <= 8, "joint low-fidelity sampling supports at most 8 augmented columns"
         offs = np.ascontiguousarray(self.augm_iterator.offset_table(), dtype=np.float64)
         if ws_bytes is None:
-            per_pt = E + E * E + max(E * (d + 2 * npl + 1) + E * (E + 1) // 2, S * (d + E + nph + 2))
+            keep, lf_pp = E + E * E, E * (d + 2 * npl + 1) + E * (E + 1) // 2
+            hf_pp = S * (d + E + nph + 2)
             slack = 256 * (2 * npl + nph + d + E + 4)
-            want = 8 * (slack + per_pt * min(M, max(1, 148 * 128 * 4 // S)))
-            ws_bytes = max(min(want, 2 << 30), 8 * (slack + per_pt))
+            # LF chunk ~2 waves of 128-column tiles, HF chunk ~4 tiles per SM (mfgp_predict_mc_delays)
+            p_lf, p_hf = min(M, 2 * 148 * 128 // E), min(M, max(1, 148 * 128 * 4 // S))
+            want = 8 * (slack + keep * p_lf + max(lf_pp * p_lf, hf_pp * p_hf))
+            ws_bytes = max(min(want, 3 << 30), 8 * (slack + keep + max(lf_pp, hf_pp)))
         ws = gp.workspace(self.device, ws_bytes)
         rc = h.lib.mfgp_predict_mc_delays(
             h.h, ctypes.byref(lf), ctypes.byref(hf), dX.data_ptr(), M,

@@ -581,46 +581,58 @@ int mfgp_predict_mc_delays(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_l
   const long long keep_pp = (long long)E + E * E;                       // mu_l, Lc survive into the HF stage
   const long long slack = 256LL * (2LL * npl + nph + D + 4);
   const long long wsd = (long long)(ws_bytes / sizeof(double));
-  long long pm = (wsd - slack) / (keep_pp + (lf_pp > hf_pp ? lf_pp : hf_pp));
-  ARG_CHECK(h, pm >= 1);
-  if (pm > M) pm = M;
-  if (pm * E > (1LL << 30) / 4) pm = (1LL << 28) / E;
-  double* mu_l = d_ws;                    // (pm, E)
-  double* Lc = mu_l + pm * E;             // (pm, E, E)
-  double* rest = Lc + pm * E * E;
+  // Two chunk levels: the low-fidelity stage runs over pmL points at a time (its scratch per point is small
+  // and its kernels want many columns), the high-fidelity stage over pmH <= pmL points of that chunk
+  // (S columns per point); mu_l / Lc of the pmL points survive in between.  Results do not depend on
+  // either size (fixed-order reductions per point).
+  long long pmL = (wsd - slack) / (keep_pp + lf_pp);
+  if (pmL > M) pmL = M;
+  if (pmL < 1 || wsd - pmL * keep_pp - slack < hf_pp)
+    pmL = (wsd - slack) / (keep_pp + (lf_pp > hf_pp ? lf_pp : hf_pp));   // one level: both stages fit per point
+  ARG_CHECK(h, pmL >= 1);
+  if (pmL > M) pmL = M;
+  if (pmL * E > (1LL << 30) / 4) pmL = (1LL << 28) / E;
+  long long pmH = (wsd - pmL * keep_pp - slack) / hf_pp;
+  ARG_CHECK(h, pmH >= 1);
+  if (pmH > pmL) pmH = pmL;
+  double* mu_l = d_ws;                    // (pmL, E)
+  double* Lc = mu_l + pmL * E;            // (pmL, E, E)
+  double* rest = Lc + pmL * E * E;
   const int prof_saved = h->prof_on;
-  for (long long m_lo = 0; m_lo < M; m_lo += pm) {
-    const long long npts = (M - m_lo < pm) ? (M - m_lo) : pm;
-    {  // low-fidelity level: joint posterior at the npts*E locations
-      const long long cols = npts * E, cols_pad = (cols + 127) / 128 * 128;
+  for (long long mL = 0; mL < M; mL += pmL) {
+    const long long nL = (M - mL < pmL) ? (M - mL) : pmL;
+    {  // low-fidelity level: joint posterior at the nL*E locations
+      const long long cols = nL * E, cols_pad = (cols + 127) / 128 * 128;
       double* locs = rest;                          // (cols, d)
       double* Ks = locs + cols_pad * d;             // (cols_pad, npl)
       double* T = Ks + cols_pad * npl;              // (npl, cols_pad)
-      double* G = T + cols_pad * npl;               // (npts, NP)
+      double* G = T + cols_pad * npl;               // (nL, NP)
       h->prof_on = 0;
-      if ((rc = build_locs_launch(h, d_Xtest + m_lo * d, npts, d, d_offs, E, tau, locs))) return rc;
+      if ((rc = build_locs_launch(h, d_Xtest + mL * d, nL, d, d_offs, E, tau, locs))) return rc;
       if ((rc = cross_gen_launch(h, kl, lf->d_X, lf->N, npl, lf->d_alpha, locs, cols, cols_pad, Ks, mu_l)))
         return rc;
       if ((rc = trmm_store(h, lf->d_W, npl, Ks, cols_pad, T))) return rc;
-      if ((rc = group_gram_launch(h, T, npl, cols_pad, npts, E, G))) return rc;
-      if ((rc = joint_chol_launch(h, G, d_kab, npts, E, (include_lf_noise ? kl.noise : 0.0) + lf_jitter,
-                                  m0 + m_lo, Lc)))
+      if ((rc = group_gram_launch(h, T, npl, cols_pad, nL, E, G))) return rc;
+      if ((rc = joint_chol_launch(h, G, d_kab, nL, E, (include_lf_noise ? kl.noise : 0.0) + lf_jitter,
+                                  m0 + mL, Lc)))
         return rc;
       h->prof_on = prof_saved;
     }
-    {  // high-fidelity level over (point, sample) columns
+    for (long long mH = mL; mH < mL + nL; mH += pmH) {   // high-fidelity level over (point, sample) columns
+      const long long npts = (mL + nL - mH < pmH) ? (mL + nL - mH) : pmH;
       const long long ncols = npts * S, cols_pad = (ncols + 127) / 128 * 128;
       double* Xq = rest;                            // (cols_pad, D)
       double* mu_c = Xq + cols_pad * D;
       double* ss = mu_c + cols_pad;
       double* Ks = ss + cols_pad;                   // (cols_pad, nph)
-      if ((rc = build_mc_rows_joint_launch(h, d_Xtest, mu_l, Lc, d_eps, seed, m0, m_lo, ncols, S, d, E, Xq)))
+      if ((rc = build_mc_rows_joint_launch(h, d_Xtest, mu_l + (mH - mL) * E, Lc + (mH - mL) * E * E, d_eps, seed,
+                                           m0, mH, ncols, S, d, E, Xq)))
         return rc;
       if ((rc = cross_gen_launch(h, kh, hf->d_X, hf->N, nph, hf->d_alpha, Xq, ncols, cols_pad, Ks, mu_c)))
         return rc;
       if ((rc = trmm_sumsq(h, hf->d_W, nph, Ks, cols_pad, ss))) return rc;
       if ((rc = finish_var_launch(h, ss, ncols, kh.kdiag, include_hf_noise ? kh.noise : 0.0, ss))) return rc;
-      if ((rc = mc_aggregate_launch(h, mu_c, ss, npts, S, d_mean + m_lo, d_var + m_lo))) return rc;
+      if ((rc = mc_aggregate_launch(h, mu_c, ss, npts, S, d_mean + mH, d_var + mH))) return rc;
     }
   }
   if (h_wsum) {
