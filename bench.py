@@ -237,6 +237,28 @@ def lml_grad_section(torch, pkg_ops, peaks, fp64_peak, n=16384):
     }
     del buf, dX, dy
     torch.cuda.empty_cache()
+    # CPU baseline for this metric: the oracle's LML+gradient on the host cores at a
+    # size it finishes in seconds, next to the GPU path at the same size
+    try:
+        from oracle import gpy_oracle as go
+        nc = 4096
+        Xc, yc = Xa[:nc], y[:nc]
+        t0 = time.perf_counter()
+        ref = go.inference(go.KIND_COMPOSITE, Xc, yc, 4, theta)
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        dXc, dyc = torch.from_numpy(Xc.copy()).cuda(), torch.from_numpy(yc.ravel().copy()).cuda()
+        bufc = pkg_ops.FactorBuffers(nc, "cuda")
+        pkg_ops.lml_grad(dXc, dyc, _ffi.KIND_COMPOSITE, 4, theta, bufc)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lml_c, g_c, _ = pkg_ops.lml_grad(dXc, dyc, _ffi.KIND_COMPOSITE, 4, theta, bufc)
+        torch.cuda.synchronize()
+        gpu_ms = 1e3 * (time.perf_counter() - t0)
+        out["cpu_baseline"] = {"n": nc, "cpu_ms_per_eval": cpu_ms, "gpu_ms_per_eval": gpu_ms, "cores": os.cpu_count(),
+                               "kind": "port", "lml_rel_diff": abs(lml_c - ref["lml"]) / abs(ref["lml"]),
+                               "grad_rel_diff": float(np.max(np.abs(g_c - ref["grad"])) / np.max(np.abs(ref["grad"])))}
+    except Exception as exc:      # the baseline is a report, not a dependency of the metric
+        out["cpu_baseline"] = {"error": repr(exc)}
     return out
 
 
