@@ -256,7 +256,7 @@ static int factor_enqueue(mfgp_ctx* h, const KParams& kp, const double* d_X, con
                             MFGP_UPLO_LOWER, npad)))
     return rc;
   if (ev) CUDA_TRY(h, cudaEventRecord(ev[1], h->stream));
-  if ((rc = potrf_padded(h, d_A, d_W, npad))) return rc;
+  if ((rc = potrf_padded(h, d_A, d_W, npad, N))) return rc;
   if (ev) CUDA_TRY(h, cudaEventRecord(ev[2], h->stream));
   if ((rc = trtri_padded(h, d_A, d_W, npad))) return rc;
   if (ev) CUDA_TRY(h, cudaEventRecord(ev[3], h->stream));
@@ -369,7 +369,7 @@ int mfgp_append_point(mfgp_handle_t h, int kind, const double* d_X, const double
 int mfgp_potrf(mfgp_handle_t h, double* d_A, double* d_W, int npad) {
   ENTER(h);
   ARG_CHECK(h, d_A && d_W);
-  int rc = potrf_padded(h, d_A, d_W, npad);
+  int rc = potrf_padded(h, d_A, d_W, npad, npad);
   if (rc) return rc;
   if ((rc = fetch_scalars(h, 1))) return rc;
   return h->h_info[0];

@@ -103,7 +103,7 @@ int make_kparams(mfgp_ctx* h, int kind, int D, int d, const double* theta, int P
 
 // ---- linalg.cu ---------------------------------------------------------------------------
 int linalg_configure(mfgp_ctx* h);
-int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad);
+int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal);   // nreal <= npad: rest is identity pad
 int trtri_padded(mfgp_ctx* h, const double* L, double* W, int npad);
 int lauum_padded(mfgp_ctx* h, const double* W, double* Kinv, int npad);
 // tmp = W[:, :]*Ks^T with fused column sum of squares:  out_ss[c] = sum_i (sum_k W[i][k] Ks[c][k])^2

@@ -33,8 +33,10 @@ constexpr int LT = 16;   // thread grid edge; 8 = LEAF / LT elements per thread 
 // to its upper positions (r <= k < c).  128 barriers per leaf instead of 256.
 template <int KB>
 __device__ __forceinline__ void leaf_fused_block(double (&t)[8][8], double (*col)[LEAF], double* dinv,
-                                                 int tx, int ty, int* info, int j0) {
-  for (int ko = 0; ko < LT; ko++) {
+                                                 int tx, int ty, int* info, int j0, int nvalid) {
+  // columns >= nvalid belong to the identity pad: L = W = I there already, no step needed
+  const int kend = min(LT, nvalid - KB * LT);
+  for (int ko = 0; ko < kend; ko++) {
     const int k = KB * LT + ko;
     double* buf = col[k & 1];
     if (tx == ko) {   // owners of column k of the packed matrix
@@ -89,7 +91,7 @@ __device__ __forceinline__ void leaf_fused_block(double (&t)[8][8], double (*col
 }
 
 __global__ void __launch_bounds__(256, 1)
-    leaf_potrf_inv_kernel(double* A, long lda, double* W, long ldw, int* info, int j0) {
+    leaf_potrf_inv_kernel(double* A, long lda, double* W, long ldw, int* info, int j0, int nvalid) {
   extern __shared__ double S[];   // LEAF x LEAF_LD staging for the coalesced write-out
   __shared__ double col[2][LEAF];
   __shared__ double dinv[LEAF];
@@ -103,14 +105,16 @@ __global__ void __launch_bounds__(256, 1)
       const int i = ty + LT * a, j = tx + LT * b;
       t[a][b] = (j <= i) ? A[(long)i * lda + j] : 0.0;
     }
-  leaf_fused_block<0>(t, col, dinv, tx, ty, info, j0);
-  leaf_fused_block<1>(t, col, dinv, tx, ty, info, j0);
-  leaf_fused_block<2>(t, col, dinv, tx, ty, info, j0);
-  leaf_fused_block<3>(t, col, dinv, tx, ty, info, j0);
-  leaf_fused_block<4>(t, col, dinv, tx, ty, info, j0);
-  leaf_fused_block<5>(t, col, dinv, tx, ty, info, j0);
-  leaf_fused_block<6>(t, col, dinv, tx, ty, info, j0);
-  leaf_fused_block<7>(t, col, dinv, tx, ty, info, j0);
+  if (tid < LEAF) dinv[tid] = 1.0;     // pad columns: 1 / L[i][i] = 1
+  __syncthreads();
+  leaf_fused_block<0>(t, col, dinv, tx, ty, info, j0, nvalid);
+  leaf_fused_block<1>(t, col, dinv, tx, ty, info, j0, nvalid);
+  leaf_fused_block<2>(t, col, dinv, tx, ty, info, j0, nvalid);
+  leaf_fused_block<3>(t, col, dinv, tx, ty, info, j0, nvalid);
+  leaf_fused_block<4>(t, col, dinv, tx, ty, info, j0, nvalid);
+  leaf_fused_block<5>(t, col, dinv, tx, ty, info, j0, nvalid);
+  leaf_fused_block<6>(t, col, dinv, tx, ty, info, j0, nvalid);
+  leaf_fused_block<7>(t, col, dinv, tx, ty, info, j0, nvalid);
   __syncthreads();   // dinv complete; col buffers free
   // stage the packed matrix, then write L and W with coalesced rows
 #pragma unroll
@@ -218,18 +222,20 @@ int trsm_rec(mfgp_ctx* h, double* A, double* W, long ld, int r0, int m, int j0, 
   return trsm_rec(h, A, W, ld, r0, m, j0 + n1, n2);
 }
 
-int potrf_rec(mfgp_ctx* h, double* A, double* W, long ld, int j0, int n) {
+// nreal: rows/columns below it are the identity pad (leaf steps there are skipped)
+int potrf_rec(mfgp_ctx* h, double* A, double* W, long ld, int j0, int n, int nreal) {
   if (n == LEAF) {
     const int smem = LEAF * LEAF_LD * 8;
     prof_begin(h, PC_LEAF);
+    const int nvalid = nreal - j0 < 0 ? 0 : (nreal - j0 > LEAF ? LEAF : nreal - j0);
     leaf_potrf_inv_kernel<<<1, 256, smem, h->stream>>>(A + (long)j0 * ld + j0, ld,
-                                                       W + (long)j0 * ld + j0, ld, h->d_info, j0);
+                                                       W + (long)j0 * ld + j0, ld, h->d_info, j0, nvalid);
     prof_end(h, PC_LEAF);
     LAUNCH_CHECK(h);
     return 0;
   }
   int n1 = split(n), n2 = n - n1, rc;
-  if ((rc = potrf_rec(h, A, W, ld, j0, n1))) return rc;
+  if ((rc = potrf_rec(h, A, W, ld, j0, n1, nreal))) return rc;
   if ((rc = trsm_rec(h, A, W, ld, j0 + n1, n2, j0, n1))) return rc;
   // A22 -= L21 L21^T on the lower tiles
   {
@@ -238,7 +244,7 @@ int potrf_rec(mfgp_ctx* h, double* A, double* W, long ld, int j0, int n) {
     p.lower_only = 1;
     if ((rc = launch_gemm<true, true>(h, p))) return rc;
   }
-  return potrf_rec(h, A, W, ld, j0 + n1, n2);
+  return potrf_rec(h, A, W, ld, j0 + n1, n2, nreal);
 }
 
 int trtri_rec(mfgp_ctx* h, const double* L, double* W, long ld, int j0, int n) {
@@ -310,7 +316,7 @@ constexpr int LA_MAXP = 64;
 // measured at N = 16384: 512 -> 55.1 ms, 768 -> 55.4, 1024 -> 56.3, 2048 -> 61.2 (profiles/r01_notes.md)
 static int la_nb(int npad) { return LA_NB_ENV ? LA_NB_ENV : (npad <= 512 * LA_MAXP ? 512 : 1024); }
 
-static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad) {
+static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
   const long ld = npad;
   cudaStream_t s_main = h->stream, s_hi = h->s_hi;
   cudaEvent_t* ev_trsm = h->ev_la;
@@ -327,7 +333,7 @@ static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad) {
     const int w = (npad - c0 < LA_NB) ? npad - c0 : LA_NB;
     const int m = npad - c0 - w;
     h->stream = s_hi;
-    rc = potrf_rec(h, A, W, ld, c0, w);
+    rc = potrf_rec(h, A, W, ld, c0, w, nreal);
     if (rc == 0 && m > 0) rc = trsm_rec(h, A, W, ld, c0 + w, m, c0, w);
     if (rc) break;
     if (m > 0) {
@@ -360,7 +366,7 @@ static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad) {
   return rc;
 }
 
-int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad) {
+int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
   ARG_CHECK(h, npad > 0 && npad % LEAF == 0);
   CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
   static int use_la = -1;
@@ -372,11 +378,11 @@ int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad) {
   }
   if (use_la && h->s_hi && npad >= LA_MIN && npad <= la_nb(npad) * LA_MAXP) {
     cudaStream_t caller = h->stream;
-    const int rc = potrf_lookahead(h, A, W, npad);
+    const int rc = potrf_lookahead(h, A, W, npad, nreal);
     h->stream = caller;   // also on the error paths inside
     return rc;
   }
-  return potrf_rec(h, A, W, npad, 0, npad);
+  return potrf_rec(h, A, W, npad, 0, npad, nreal);
 }
 
 // Level-synchronous form of trtri_rec for npad = 128 * 2^q: the nodes of one level are independent and
