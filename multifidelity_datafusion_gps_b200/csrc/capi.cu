@@ -1,5 +1,6 @@
 // extern "C" entry points declared in include/mfgp_b200.h: argument checks, scratch layout,
 // chunk loops and stream ordering.  No torch types, no allocation outside mfgp_create.
+#include <stdlib.h>
 #include "common.cuh"
 
 // launchers defined in predict.cu
@@ -100,6 +101,19 @@ int make_kparams(mfgp_ctx* h, int kind, int D, int d, const double* theta, int P
   return 0;
 }
 
+// Up to this size the single-CTA kernel beats the multi-kernel chain (wall time per LML+gradient evaluation:
+// N = 8: 66 vs 92 us, N = 30: 78 vs 108 us, N = 100: 147 vs 144 us; tools/fit_time.py)
+#define MFGP_SMALL_N 96
+// MFGP_SMALL_PATH=0 routes these sizes through the multi-kernel chain as well (A/B and parity checks)
+static bool small_path() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFGP_SMALL_PATH");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int fetch_scalars(mfgp_ctx* h, int ndoubles) {
   CUDA_TRY(h, cudaMemcpyAsync(h->h_pinned, h->d_scalars, ndoubles * sizeof(double),
                               cudaMemcpyDeviceToHost, h->stream));
@@ -161,7 +175,7 @@ int mfgp_create(int device, mfgp_handle_t* out) {
     for (int j = 0; j < 256; j++) tbl[j] = (double)exp2l((long double)j / 256.0L);
     ok = cudaMemcpy(h->d_exp_tbl, tbl, sizeof(tbl), cudaMemcpyHostToDevice) == cudaSuccess;
   }
-  if (!ok || linalg_configure(h) != 0 || assemble_configure(h) != 0 || predict_configure(h) != 0) {
+  if (!ok || small_gp_configure(h) != 0 || linalg_configure(h) != 0 || assemble_configure(h) != 0 || predict_configure(h) != 0) {
     snprintf(g_err, sizeof(g_err), "mfgp_create: scratch allocation / kernel configuration failed: %s",
              cudaGetErrorString(cudaGetLastError()));
     delete h;
@@ -274,7 +288,13 @@ int mfgp_factorize(mfgp_handle_t h, int kind, const double* d_X, const double* d
   KParams kp;
   int rc = make_kparams(h, kind, D, d, h_theta, P, &kp);
   if (rc) return rc;
-  if ((rc = factor_enqueue(h, kp, d_X, d_y, N, jitter, d_A, d_W, d_alpha, nullptr))) return rc;
+  if (N <= MFGP_SMALL_N && small_path()) {
+    if ((rc = small_gp_launch(h, kp, d_X, d_y, N, kp.noise + JITTER_CONST + jitter, d_A, d_W, d_alpha,
+                              h->d_scalars, 0)))
+      return rc;
+  } else if ((rc = factor_enqueue(h, kp, d_X, d_y, N, jitter, d_A, d_W, d_alpha, nullptr))) {
+    return rc;
+  }
   if ((rc = fetch_scalars(h, 3))) return rc;
   if (h_out) {
     h_out[0] = h->h_pinned[0];
@@ -310,6 +330,17 @@ int mfgp_lml_grad_timed(mfgp_handle_t h, int kind, const double* d_X, const doub
   int rc = make_kparams(h, kind, D, d, h_theta, P, &kp);
   if (rc) return rc;
   const int npad = mfgp_padded_n(N);
+  if (N <= MFGP_SMALL_N && small_path()) {   // one fused launch; no per-stage times
+    if ((rc = small_gp_launch(h, kp, d_X, d_y, N, kp.noise + JITTER_CONST + jitter, d_A, d_W, d_alpha,
+                              h->d_scalars, 1)))
+      return rc;
+    if ((rc = fetch_scalars(h, 16))) return rc;
+    if (h_lml) h_lml[0] = h->h_pinned[0];
+    if (h_grad) grads_from_sums(kp, h->h_pinned + 8, h_grad);
+    if (h_ms)
+      for (int i = 0; i < 6; i++) h_ms[i] = 0.0;
+    return h->h_info[0];
+  }
   cudaEvent_t* ev = h_ms ? h->ev : nullptr;
   if ((rc = factor_enqueue(h, kp, d_X, d_y, N, jitter, d_A, d_W, d_alpha, ev))) return rc;
   if ((rc = lauum_padded(h, d_W, d_A, npad))) return rc;

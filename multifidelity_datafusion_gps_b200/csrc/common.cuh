@@ -110,6 +110,9 @@ int lauum_padded(mfgp_ctx* h, const double* W, double* Kinv, int npad);
 int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad,
                double* out_ss);
 
+int small_gp_launch(mfgp_ctx* h, const KParams& kp, const double* X, const double* y, int N, double diag_add,
+                    double* A, double* W, double* alpha, double* d_out, int want_grad);
+int small_gp_configure(mfgp_ctx* h);
 int trmm_store(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad, double* T);
 
 // ---- assemble.cu -------------------------------------------------------------------------

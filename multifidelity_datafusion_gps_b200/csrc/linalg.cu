@@ -11,6 +11,7 @@
 //   lauum:     Kinv = W^T W, one launch over the lower tiles with k >= row0
 #include <stdlib.h>
 #include "gemm.cuh"
+#include "fastmath.cuh"
 
 namespace {
 
@@ -137,6 +138,194 @@ __global__ void __launch_bounds__(256, 1)
     }
     A[(long)i * lda + j] = l;
     W[(long)i * ldw + j] = w;
+  }
+}
+
+
+// ---- N <= 128: the whole LML (+ gradient) evaluation in ONE kernel -----------------------------------
+// The reference's own problems are tiny (5-30 high-fidelity points, src/gpc/mfgp_gpc.py:10,18-20, refitted
+// by up to 7 L-BFGS-B runs per adaptation step), where the chain assemble -> leaf -> solves -> W^T W ->
+// gradient reduction -> reduce was eight launches of ~10 us each plus their gaps.  One CTA does it all:
+// K_y is assembled straight into the leaf's register tile, factorised and inverted there (steps over
+// the identity pad skipped), and alpha, log det, K^-1 = W^T W and the six gradient sums come out of
+// shared memory.  Same arithmetic per element as the large-N kernels (exp2s, direct-form distances).
+constexpr int SMALL_SMEM_FIXED = (fm::EXP_TBL_DOUBLES + LEAF * LEAF_LD + 6 * LEAF + 64) * 8;
+
+__device__ __forceinline__ void small_kernel_parts(const KParams& kp, const double* sX, int i, int j, unsigned tbl,
+                                                   double& rx, double& rz, double& k12, double& k3) {
+  rx = 0.0;
+  rz = 0.0;
+  for (int dd = 0; dd < kp.D; dd++) {
+    const double t = sX[dd * LEAF + i] - sX[dd * LEAF + j];
+    if (dd < kp.d) rx = fma(t, t, rx);
+    else rz = fma(t, t, rz);
+  }
+  k12 = fm::exp2s(fma(kp.uz, rz, fma(kp.ux, rx, kp.lc12)), tbl);
+  k3 = kp.s3 != 0.0 ? fm::exp2s(fma(kp.u3, rx, kp.ls3), tbl) : 0.0;
+}
+
+__global__ void __launch_bounds__(256, 1)
+    small_gp_kernel(KParams kp, const double* __restrict__ X, const double* __restrict__ y, int N,
+                    double diag_add, double* __restrict__ A, double* __restrict__ W,
+                    double* __restrict__ alpha, double* __restrict__ out, int* info, int want_grad) {
+  extern __shared__ __align__(16) double sm[];
+  double* stbl = sm;                                   // exp table (32 KB)
+  double* S = stbl + fm::EXP_TBL_DOUBLES;              // [128][129] packed matrix
+  double* dinv = S + LEAF * LEAF_LD;                   // [128]
+  double* sy = dinv + LEAF;                            // [128]
+  double* sv = sy + LEAF;                              // [128]
+  double* sal = sv + LEAF;                             // [128]
+  double (*col)[LEAF] = reinterpret_cast<double (*)[LEAF]>(sal + LEAF);   // [2][128]... uses 2*LEAF
+  double* red = sal + LEAF + 2 * LEAF;                 // [64]
+  double* sX = red + 64;                               // [D][128]
+  const int tid = threadIdx.x, tx = tid & (LT - 1), ty = tid >> 4;
+  const int lane = tid & 31, warp = tid >> 5;
+  fm::load_exp_table(stbl, kp.exp_tbl);
+  const unsigned tbl = fm::lane_table(stbl);
+  for (int idx = tid; idx < LEAF * kp.D; idx += 256) {
+    const int r = idx / kp.D, dd = idx - r * kp.D;
+    sX[dd * LEAF + r] = r < N ? X[idx] : 0.0;
+  }
+  if (tid < LEAF) {
+    sy[tid] = tid < N ? y[tid] : 0.0;
+    dinv[tid] = 1.0;
+  }
+  __syncthreads();
+  // K_y into the packed register tile (lower positions; identity on the pad)
+  double t[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int i = ty + LT * a, j = tx + LT * b;
+      double v = 0.0;
+      if (j <= i) {
+        if (i < N) {
+          double rx, rz, k12, k3;
+          small_kernel_parts(kp, sX, i, j, tbl, rx, rz, k12, k3);
+          v = k12 + k3 + (i == j ? diag_add : 0.0);
+        } else {
+          v = (i == j) ? 1.0 : 0.0;
+        }
+      }
+      t[a][b] = v;
+    }
+  leaf_fused_block<0>(t, col, dinv, tx, ty, info, 0, N);
+  leaf_fused_block<1>(t, col, dinv, tx, ty, info, 0, N);
+  leaf_fused_block<2>(t, col, dinv, tx, ty, info, 0, N);
+  leaf_fused_block<3>(t, col, dinv, tx, ty, info, 0, N);
+  leaf_fused_block<4>(t, col, dinv, tx, ty, info, 0, N);
+  leaf_fused_block<5>(t, col, dinv, tx, ty, info, 0, N);
+  leaf_fused_block<6>(t, col, dinv, tx, ty, info, 0, N);
+  leaf_fused_block<7>(t, col, dinv, tx, ty, info, 0, N);
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) S[(ty + LT * a) * LEAF_LD + tx + LT * b] = t[a][b];
+  __syncthreads();
+  // upper positions: accumulators -> W itself, S[j][i] = W[i][j] (j < i); then L and W go to global memory
+  for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
+    const int i = idx >> 7, j = idx & 127;
+    if (j < i) S[j * LEAF_LD + i] *= -dinv[i];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < LEAF * LEAF; idx += 256) {
+    const int i = idx >> 7, j = idx & 127;
+    double l = 0.0, w = 0.0;
+    if (j < i) { l = S[i * LEAF_LD + j]; w = S[j * LEAF_LD + i]; }
+    else if (j == i) { l = S[i * LEAF_LD + i]; w = dinv[i]; }
+    if (!want_grad) A[(long)i * LEAF + j] = l;       // with the gradient, A receives K^-1 below
+    W[(long)i * LEAF + j] = w;
+  }
+  // v = W y, alpha = W^T v (threads 0..127, one row / column each; conflict-free strides)
+  if (tid < LEAF) {
+    double acc = 0.0;
+    if (tid < N) {
+      for (int k = 0; k < tid; k++) acc = fma(S[k * LEAF_LD + tid], sy[k], acc);
+      acc = fma(dinv[tid], sy[tid], acc);
+    }
+    sv[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < LEAF) {
+    double acc = 0.0;
+    if (tid < N) {
+      acc = dinv[tid] * sv[tid];
+      for (int i = tid + 1; i < N; i++) acc = fma(S[tid * LEAF_LD + i], sv[i], acc);
+    }
+    sal[tid] = acc;
+    alpha[tid] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {   // log det and y^T alpha, fixed order
+    double ld = 0.0, ya = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      ld -= log(dinv[i]);
+      ya = fma(sy[i], sal[i], ya);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ld += __shfl_xor_sync(0xffffffffu, ld, o);
+      ya += __shfl_xor_sync(0xffffffffu, ya, o);
+    }
+    if (lane == 0) {
+      const double logdet = 2.0 * ld;
+      out[1] = logdet;
+      out[2] = ya;
+      out[0] = 0.5 * (-(double)N * 1.8378770664093453 - logdet - ya);
+    }
+  }
+  if (!want_grad) return;
+  // K^-1 = W^T W on the lower positions and the six gradient sums in the same sweep
+  double G6[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+  for (int a = 0; a < 8; a++) {
+    const int i = ty + LT * a;
+#pragma unroll 1
+    for (int b = 0; b <= a; b++) {
+      const int j = tx + LT * b;
+      double kin = 0.0;
+      if (j <= i) {
+        if (i < N) {
+          // sum_{k > i} W[k][i] W[k][j] + W[i][i] W[i][j]
+          double acc = dinv[i] * (j < i ? S[j * LEAF_LD + i] : dinv[i]);
+          for (int k = i + 1; k < N; k++) acc = fma(S[i * LEAF_LD + k], S[j * LEAF_LD + k], acc);
+          kin = acc;
+          double rx, rz, k12, k3;
+          small_kernel_parts(kp, sX, i, j, tbl, rx, rz, k12, k3);
+          const double wgt = (i == j) ? 0.5 : 1.0;      // G = 0.5 (aa^T - K^-1); off-diagonal counted twice
+          const double G = wgt * fma(sal[i], sal[j], -kin);
+          const double gk = G * k12, g3 = G * k3;
+          G6[0] += gk;
+          G6[1] = fma(gk, rz, G6[1]);
+          G6[2] = fma(gk, rx, G6[2]);
+          G6[3] += g3;
+          G6[4] = fma(g3, rx, G6[4]);
+          if (i == j) G6[5] += G;
+        } else {
+          kin = (i == j) ? 1.0 : 0.0;
+        }
+        A[(long)i * LEAF + j] = kin;
+      } else {
+        A[(long)i * LEAF + j] = 0.0;
+      }
+    }
+  }
+  // upper blocks of A that the loop above did not visit (b > a) are left as they were: only the lower
+  // triangle of K^-1 is defined, as after the large-N path
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    double v = G6[q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp * 6 + q] = v;
+  }
+  __syncthreads();
+  if (tid < 6) {
+    double v = 0.0;
+    for (int w = 0; w < 8; w++) v += red[w * 6 + tid];
+    out[8 + tid] = v;
   }
 }
 
@@ -456,5 +645,26 @@ int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long lo
                                      dg::Big::SMEM_BYTES, h->stream>>>(W, npad, Ks, out_ss);
   prof_end(h, PC_TRMM_SUMSQ);
   LAUNCH_CHECK(h);
+  return 0;
+}
+
+
+// N <= 128: one fused launch (see small_gp_kernel).  d_A, d_W are 128 x 128 (ld 128), d_alpha 128;
+// d_out: [0..2] = {LML, logdet, y^T alpha}, [8..13] = the six gradient sums (want_grad).
+int small_gp_launch(mfgp_ctx* h, const KParams& kp, const double* X, const double* y, int N, double diag_add,
+                    double* A, double* W, double* alpha, double* d_out, int want_grad) {
+  ARG_CHECK(h, N >= 1 && N <= LEAF);
+  const size_t smem = SMALL_SMEM_FIXED + (size_t)kp.D * LEAF * sizeof(double);
+  CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
+  prof_begin(h, PC_LEAF);
+  small_gp_kernel<<<1, 256, smem, h->stream>>>(kp, X, y, N, diag_add, A, W, alpha, d_out, h->d_info, want_grad);
+  prof_end(h, PC_LEAF);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int small_gp_configure(mfgp_ctx* h) {
+  CUDA_TRY(h, cudaFuncSetAttribute(small_gp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   SMALL_SMEM_FIXED + MFGP_MAX_D * LEAF * (int)sizeof(double)));
   return 0;
 }

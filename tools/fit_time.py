@@ -1,0 +1,31 @@
+import sys, time
+sys.path.insert(0, "/root/repo")
+import numpy as np
+import multifidelity_datafusion_gps_b200 as pkg
+from oracle import mfgp_oracle as mo
+from tests import util
+rs = np.random.RandomState(10)
+X = rs.uniform(size=(8, 2))
+m = pkg.NARGP(2, util.hf_2d, util.lf_2d)
+np.random.seed(1); t = time.perf_counter(); m.fit(X); dt = time.perf_counter() - t
+print("GPU fit: %.3f s, %d evals, %.1f us/eval" % (dt, m.hf_model.n_evals, 1e6 * dt / m.hf_model.n_evals))
+o = mo.OracleMFGP(2, 0, 0, util.hf_2d, f_low=util.lf_2d)
+np.random.seed(1); t = time.perf_counter(); o.fit(X); dt = time.perf_counter() - t
+print("CPU oracle fit: %.3f s, %d evals, %.1f us/eval" % (dt, o.hf_model.n_evals, 1e6 * dt / o.hf_model.n_evals))
+import cProfile, pstats
+np.random.seed(1)
+pr = cProfile.Profile(); pr.enable(); m.fit(X); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
+
+# steady-state evaluation rate at tiny N (wall clock, after warm-up)
+for n in (8, 30, 100, 128):
+    Xn = rs.uniform(size=(n, 2))
+    mm = pkg.NARGP(2, util.hf_2d, util.lf_2d)
+    mm.fit(Xn, theta=np.array([1.0, 0.8, 1.0, 0.5, 0.1, 0.3, 1e-3]))
+    th = mm.hf_model.param_array
+    for _ in range(20):
+        mm.hf_model.lml_and_grad(th)
+    t = time.perf_counter()
+    for _ in range(200):
+        mm.hf_model.lml_and_grad(th)
+    print("N=%d: %.1f us per LML+grad evaluation (wall)" % (n, 1e6 * (time.perf_counter() - t) / 200))
