@@ -127,7 +127,7 @@ def test_potrf_reports_first_bad_pivot(T):
 
 
 @pytest.mark.parametrize("kind,d,E", CASES)
-@pytest.mark.parametrize("N", [1, 10, 30, 200, 700])
+@pytest.mark.parametrize("N", [1, 2, 10, 30, 96, 97, 128, 200, 700])   # <= 96: fused single-CTA kernel
 def test_lml_and_gradient_match_oracle(T, kind, d, E, N):
     X, Y, th = util.random_case(100 + N, N, d, E, kind)
     buf = T.ops.FactorBuffers(N, T.dev)
@@ -140,6 +140,14 @@ def test_lml_and_gradient_match_oracle(T, kind, d, E, N):
         assert util.rel_err(buf.alpha.cpu().numpy()[:N], ref["alpha"].ravel()) < max(tol, 1e-8)
         Ki = np.tril(buf.A.cpu().numpy())[:N, :N]
         assert util.rel_err(Ki, np.tril(ref["Ki"])) < max(tol, 1e-8)
+    # the posterior left behind serves predictions (W = L^-1, alpha), whichever kernel produced it
+    lvl = T.ops.LevelRef(T.up(X), kind, d, th, buf)
+    Xs = np.random.default_rng(N).uniform(size=(33, d + E))
+    mean, var = T.ops.predict(lvl, T.up(Xs), True, True)
+    ref = go.inference(kind, X, Y, d, th, form="direct", want_grad=False)
+    mu_ref, var_ref = go.posterior_predict(kind, X, d, th, ref["L"], ref["alpha"], Xs, True, form="direct")
+    assert util.rel_err(mean.cpu().numpy(), mu_ref.ravel(), max(np.max(np.abs(mu_ref)), 1e-3)) < 1e-8
+    assert util.rel_err(var.cpu().numpy(), var_ref.ravel(), 1.5) < 1e-6
 
 
 @pytest.mark.parametrize("kind,d,E", CASES)
