@@ -456,6 +456,21 @@ def main():
                                    "ms": float(np.mean(acq_ms)),
                                    "candidates_per_s": float(M / (np.mean(acq_ms) * 1e-3)),
                                    "argmax_index": int(c_idx), "max_variance": float(c_val)}
+            if not args.no_cpu:
+                # CPU baseline: the oracle's vectorised predict + np.argmax on a bounded sample of the candidates
+                from oracle import mfgp_oracle as mo
+                o = mo.OracleMFGP(4, 0, 0, hf_4d, lf_X=wl["Xl"], lf_Y=wl["yl"], lf_theta=wl["lf_theta"])
+                o.fit(wl["Xh"], theta=wl["hf_theta"])
+                o.lf_model.posterior(); o.hf_model.posterior()
+                nc = 8192
+                t0 = time.perf_counter()
+                v_ref = o.predict(wl["Xt"][M - nc:])[1].ravel()
+                i_ref = int(np.argmax(v_ref))
+                dt = time.perf_counter() - t0
+                line["acquisition"]["cpu_baseline"] = {
+                    "candidates_per_s": nc / dt, "cores": os.cpu_count(), "kind": "port",
+                    "sample": "last %d of %d candidates, NumPy/SciPy oracle" % (nc, M), "seconds": dt,
+                    "argmax_agrees_on_sample": bool(M - nc + i_ref == int(c_idx)) if int(c_idx) >= M - nc else None}
             del dX
             gp._ws_pool.clear()
             torch.cuda.empty_cache()
