@@ -9,7 +9,7 @@ to the next level through the ``device_predict`` hook of ``MultifidelityDataFusi
 """
 import numpy as np
 
-from .NARGP import NARGP
+from ._presets import NARGP
 
 
 class _LevelMean:
