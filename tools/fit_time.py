@@ -1,17 +1,14 @@
+"""Wall time of a full fit (7 L-BFGS-B runs) and of single LML+gradient evaluations at tiny N on the GPU."""
 import sys, time
 sys.path.insert(0, "/root/repo")
 import numpy as np
 import multifidelity_datafusion_gps_b200 as pkg
-from oracle import mfgp_oracle as mo
 from tests import util
 rs = np.random.RandomState(10)
 X = rs.uniform(size=(8, 2))
 m = pkg.NARGP(2, util.hf_2d, util.lf_2d)
 np.random.seed(1); t = time.perf_counter(); m.fit(X); dt = time.perf_counter() - t
 print("GPU fit: %.3f s, %d evals, %.1f us/eval" % (dt, m.hf_model.n_evals, 1e6 * dt / m.hf_model.n_evals))
-o = mo.OracleMFGP(2, 0, 0, util.hf_2d, f_low=util.lf_2d)
-np.random.seed(1); t = time.perf_counter(); o.fit(X); dt = time.perf_counter() - t
-print("CPU oracle fit: %.3f s, %d evals, %.1f us/eval" % (dt, o.hf_model.n_evals, 1e6 * dt / o.hf_model.n_evals))
 import cProfile, pstats
 np.random.seed(1)
 pr = cProfile.Profile(); pr.enable(); m.fit(X); pr.disable()
