@@ -1,9 +1,24 @@
 """Wall time of a full fit (7 L-BFGS-B runs) and of single LML+gradient evaluations at tiny N on the GPU."""
 import sys, time
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import multifidelity_datafusion_gps_b200 as pkg
-from tests import util
+
+A2 = [2.2 * np.pi, np.pi]                       # reference tests/test_mfgp_adapt_2d.py:9-19
+
+
+class util:
+    @staticmethod
+    def hf_2d(x):
+        x = np.atleast_2d(x)
+        return (np.sin(x[:, 0] * A2[0]) * np.sin(x[:, 1] * A2[1]))[:, None]
+
+    @staticmethod
+    def lf_2d(x):
+        x = np.atleast_2d(x)
+        return util.hf_2d(x) - 1.2 * (np.sin(x[:, 0] * np.pi * 0.1) + np.sin(x[:, 1] * np.pi * 0.1))[:, None]
+
 rs = np.random.RandomState(10)
 X = rs.uniform(size=(8, 2))
 m = pkg.NARGP(2, util.hf_2d, util.lf_2d)
