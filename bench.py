@@ -415,9 +415,9 @@ def main():
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp64_peak if fp64_peak else None,
                     # DRAM read+write per launch from the ncu --set full capture of this kernel
-                    # (profiles/r01_ncu_mc_kernels_v3.txt: 1.616 GB for 75 776 columns at N_h = 1024),
+                    # (profiles/r01_ncu_mc_hf_kernels_v6.txt: 1.651 GB for 75 776 columns at N_h = 1024),
                     # scaled to this run's columns per launch
-                    "traffic": (1.616e9 / 75776.0 * cols_per_launch) if args.nh == 1024 else None,
+                    "traffic": (1.651e9 / 75776.0 * cols_per_launch) if args.nh == 1024 else None,
                     "avg_launch_ms": trmm_ms, "launches_per_step": hf_launches_per_step,
                     "flops_per_launch": flops_per_launch,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no FP64 "
