@@ -31,17 +31,22 @@ def build(force=False, verbose=False):
     """Compile every CUDA source into one shared library.  Returns the library path."""
     if not force and not needs_build():
         return LIB
-    objs = []
-    log = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("nvcc failed on %s" % src)
-        objs.append(obj)
+        return src, obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    objs = []
+    log = []
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:      # the translation units are independent
+        for src, obj, r in pool.map(compile_one, SOURCES):
+            log.append(r.stderr)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed on %s" % src)
+            objs.append(obj)
     cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
