@@ -253,3 +253,111 @@ def test_oracle_orchestration_reproduces_the_executed_reference(name):
     tol_f = 1e-7 if sc.get("data_driven") else 1e-10
     assert np.allclose(mean_f, g[name + "/mean_fixed"], rtol=tol_f, atol=1e-2 * tol_f)
     assert np.allclose(var_f, g[name + "/var_fixed"], rtol=tol_f, atol=1e-2 * tol_f)
+
+
+# ---- third-party cross-check of the GPy restatement: scikit-learn's exact GP ----
+# GPy cannot run here, but sklearn ships an independent exact-GP implementation
+# (GaussianProcessRegressor.log_marginal_likelihood(theta, eval_gradient=True), predict(return_std=True),
+# product / sum kernels).  It pins the arithmetic the reference reaches through
+# GPy.models.GPRegression (src/MFDataFusion.py:93-100,156, src/abstractMFGP.py:131-137): LML, its
+# gradient with respect to all hyper-parameters including the noise, and the predictive moments.
+def _sklearn_kernel(kind, d, D, theta):
+    from sklearn.gaussian_process import kernels as sk
+
+    class Columns(sk.Kernel):
+        """base kernel applied to a subset of the input columns (GPy's active_dims,
+        src/abstractMFGP.py:74-79); hyper-parameters are the base kernel's."""
+
+        def __init__(self, kernel, cols):
+            self.kernel, self.cols = kernel, tuple(cols)
+
+        def get_params(self, deep=True):
+            params = dict(kernel=self.kernel, cols=self.cols)
+            if deep:
+                params.update(("kernel__" + k, v) for k, v in self.kernel.get_params().items())
+            return params
+
+        @property
+        def hyperparameters(self):
+            return [sk.Hyperparameter("kernel__" + h.name, h.value_type, h.bounds, h.n_elements)
+                    for h in self.kernel.hyperparameters]
+
+        @property
+        def theta(self):
+            return self.kernel.theta
+
+        @theta.setter
+        def theta(self, theta):
+            self.kernel.theta = theta
+
+        @property
+        def bounds(self):
+            return self.kernel.bounds
+
+        def __eq__(self, other):
+            return type(self) is type(other) and self.kernel == other.kernel and self.cols == other.cols
+
+        def __call__(self, X, Y=None, eval_gradient=False):
+            c = list(self.cols)
+            return self.kernel(X[:, c], None if Y is None else Y[:, c], eval_gradient=eval_gradient)
+
+        def diag(self, X):
+            return self.kernel.diag(X[:, list(self.cols)])
+
+        def is_stationary(self):
+            return self.kernel.is_stationary()
+
+    C = lambda v: sk.ConstantKernel(v, constant_value_bounds=(1e-10, 1e10))
+    R = lambda l: sk.RBF(l, length_scale_bounds=(1e-10, 1e10))
+    W = sk.WhiteKernel(theta[-1], noise_level_bounds=(1e-12, 1e10))
+    if kind == go.KIND_RBF:
+        return C(theta[0]) * R(theta[1]) + W
+    x, z = range(d), range(d, D)
+    return (C(theta[0]) * Columns(R(theta[1]), z)) * (C(theta[2]) * Columns(R(theta[3]), x)) \
+        + C(theta[4]) * Columns(R(theta[5]), x) + W
+
+
+@pytest.mark.parametrize("kind,d,E,N", [(go.KIND_RBF, 3, 0, 60), (go.KIND_RBF, 2, 5, 45),
+                                        (go.KIND_COMPOSITE, 1, 1, 50), (go.KIND_COMPOSITE, 2, 5, 80),
+                                        (go.KIND_COMPOSITE, 4, 1, 120)])
+def test_gpy_oracle_against_sklearn(kind, d, E, N):
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    X, Y, th = util.random_case(11, N, d, E, kind, noise=3e-2)
+    Xs = np.random.default_rng(12).uniform(size=(37, d + E))
+    kern = _sklearn_kernel(kind, d, d + E, th)
+    # theta order of the compound kernel = ours: [s1, l1 | s2, l2 | s3, l3 | noise] (k1.theta then k2.theta)
+    assert np.allclose(np.exp(kern.theta), th, rtol=1e-14)
+    gpr = GaussianProcessRegressor(kernel=kern, alpha=go.JITTER_CONST, optimizer=None, normalize_y=False)
+    gpr.fit(X, Y.ravel())                           # K + noise I (WhiteKernel) + 1e-8 I (alpha): GPy's K_y
+    lml_sk, g_sk = gpr.log_marginal_likelihood(kern.theta, eval_gradient=True)
+    mu_sk, sd_sk = gpr.predict(Xs, return_std=True)
+    for form, tol in (("direct", 1e-10), ("gpy", 1e-8)):     # sklearn computes distances in the direct form
+        res = go.inference(kind, X, Y, d, th, form=form)
+        assert abs(res["lml"] - lml_sk) <= tol * abs(lml_sk)
+        # sklearn differentiates with respect to log(theta): d/dlog(t) = t d/dt
+        assert np.max(np.abs(res["grad"] * th - g_sk)) <= 100 * tol * max(1.0, np.max(np.abs(g_sk)))
+        mu, var = go.posterior_predict(kind, X, d, th, res["L"], res["alpha"], Xs, include_noise=True, form=form)
+        assert np.max(np.abs(mu.ravel() - mu_sk)) <= 100 * tol * np.max(np.abs(mu_sk))
+        assert np.max(np.abs(var.ravel() - sd_sk ** 2)) <= 100 * tol * np.max(sd_sk ** 2)
+
+
+def test_gpy_oracle_model_predict_against_sklearn_fitted_by_the_oracle():
+    # end to end through OracleGPRegression (the LF level, src/abstractMFGP.py:100-104): the optimiser's end
+    # point, re-evaluated by sklearn at the same hyper-parameters
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    rs = np.random.RandomState(10)
+    X = rs.uniform(size=(40, 2))
+    Y = util.lf_2d(X)
+    m = go.OracleGPRegression(X, Y)
+    m.optimize()
+    th = np.maximum(m.theta, [1e-9, 1e-9, 1e-11])
+    m.theta = th
+    m._post = None
+    kern = _sklearn_kernel(go.KIND_RBF, 2, 2, th)
+    gpr = GaussianProcessRegressor(kernel=kern, alpha=go.JITTER_CONST, optimizer=None).fit(X, Y.ravel())
+    assert abs(m.log_likelihood() - gpr.log_marginal_likelihood(kern.theta)) <= 1e-7 * abs(m.log_likelihood())
+    Xs = rs.uniform(size=(25, 2))
+    mu, var = m.predict(Xs)
+    mu_sk, sd_sk = gpr.predict(Xs, return_std=True)
+    assert np.max(np.abs(mu.ravel() - mu_sk)) <= 1e-6 * np.max(np.abs(mu_sk))
+    assert np.max(np.abs(var.ravel() - sd_sk ** 2)) <= 1e-6 * np.max(sd_sk ** 2)
