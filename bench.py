@@ -2,22 +2,37 @@
 """bench.py -- headline benchmark of the multi-fidelity GP hot path on B200.
 
 Metric (BASELINE.json): MC predictive samples/s = test points x MC samples pushed through the
-NARGP 2-level posterior per second, plus (N=1 only) LML+gradient evaluations/s at N=16384.
+NARGP 2-level posterior per second, plus (N=1 only) LML+gradient evaluations/s at N=16384, the
+acquisition arg-max, the config-5 sweep, a fit/adapt run at the reference's own sizes and CPU baselines.
 
 A "step" is one pass of the hot path over one batch: predict_mc on the full test batch
 (M = 32^4 = 1 048 576 tensor Gauss-Legendre nodes x S = 100 low-fidelity posterior samples, PCE mean
-reduced at the end).  Multi-GPU: weak scaling -- every rank processes its own batch of M points (global
-point indices rank*M ..), no data-path collective; the only collectives are the one-off NCCL broadcast
-of the factorised state (untimed, reported) and one all_reduce of the PCE-mean scalar per step.
+reduced at the end).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-                  [--nh 1024 --nl 4096 --m 1048576 --s 100] [--no-lml]
+Multi-GPU: STRONG scaling by default -- the SAME M nodes are split contiguously
+over the ranks (rank r owns dist.shard_range(M, r, world), Philox counters keyed by the global point
+index), no data-path collective; the only collectives are the one-off NCCL broadcast of the factorised
+state (untimed, reported) and one all_reduce of the PCE-mean scalar per step.  `--scaling weak` gives
+every rank its own batch of M points instead (reported as a secondary block in the default run).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling strong|weak]
+                  [--nh 1024 --nl 4096 --points 1048576 --samples 100] [--no-lml] [--no-cpu] [--no-extras]
 """
+import os
+import sys
+
+if "reference" in sys.argv or os.environ.get("TORCHELASTIC_RUN_ID"):
+    # torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin the CPU arm (and rank 0's CPU
+    # baselines) to ONE BLAS thread.  Must happen before NumPy loads OpenBLAS.
+    _n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if "reference" not in sys.argv:
+        _n = max(1, _n // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_n)
+
 import argparse
 import json
-import os
 import subprocess
-import sys
 import threading
 import time
 
@@ -28,6 +43,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PI = np.pi
+A2 = [2.2 * PI, PI]
 
 
 def hf_4d(x):                    # reference tests/test_mfgp_adapt_4d.py:13-15
@@ -37,6 +53,26 @@ def hf_4d(x):                    # reference tests/test_mfgp_adapt_4d.py:13-15
 def lf_4d(x):                    # reference tests/test_mfgp_adapt_4d.py:18-21
     return hf_4d(x) - 0.25 * (np.sin(x[:, 0] * PI * 0.1) + np.sin(x[:, 1] * PI * 0.05)
                               + np.sin(x[:, 2] * 0.15 * PI) + np.sin(x[:, 3] * 0.2 * PI))[:, None]
+
+
+def hf_2d(x):                    # reference tests/test_mfgp_adapt_2d.py:12-14
+    x = np.atleast_2d(x)
+    return (np.sin(x[:, 0] * A2[0]) * np.sin(x[:, 1] * A2[1]))[:, None]
+
+
+def lf_2d(x):                    # reference tests/test_mfgp_adapt_2d.py:17-19
+    x = np.atleast_2d(x)
+    return hf_2d(x) - 1.2 * (np.sin(x[:, 0] * PI * 0.1) + np.sin(x[:, 1] * PI * 0.1))[:, None]
+
+
+def blas_threads():
+    """Threads the host BLAS really uses (threadpoolctl), not os.cpu_count()."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [d["num_threads"] for d in threadpool_info() if d.get("user_api") == "blas"]
+        return int(max(n)) if n else 1
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", "1"))
 
 
 def gauss_legendre_grid(n_per_dim, dim):
@@ -49,19 +85,19 @@ def gauss_legendre_grid(n_per_dim, dim):
     return np.ascontiguousarray(nodes), np.ascontiguousarray(weights)
 
 
-def workload(args):
+def workload(nh, nl, m):
     """Synthetic config-5 model: d = 4, U[0,1]^4 training inputs (default_rng(1)),
     y_l = lf_4d, y_h = hf_4d, fixed hyper-parameters (config 4), test set = tensor Gauss-Legendre grid."""
     rng = np.random.default_rng(1)
-    Xh = rng.uniform(size=(args.nh, 4))
-    Xl = rng.uniform(size=(args.nl, 4))
+    Xh = rng.uniform(size=(nh, 4))
+    Xl = rng.uniform(size=(nl, 4))
     yh, yl = hf_4d(Xh), lf_4d(Xl)
-    n1 = int(round(args.m ** 0.25))
-    if n1 ** 4 == args.m:
+    n1 = int(round(m ** 0.25))
+    if n1 ** 4 == m:
         Xt, w = gauss_legendre_grid(n1, 4)
     else:
-        Xt = np.random.default_rng(3).uniform(size=(args.m, 4))
-        w = np.full(args.m, 1.0 / args.m)
+        Xt = np.random.default_rng(3).uniform(size=(m, 4))
+        w = np.full(m, 1.0 / m)
     lf_theta = np.array([1.0, 0.3, 0.01 * yl.var()])
     hf_theta = np.array([1.0, 0.3, 1.0, 0.3, 0.1, 0.3, 0.01 * yh.var()])
     return dict(Xh=Xh, Xl=Xl, yh=yh, yl=yl, Xt=Xt, w=w, lf_theta=lf_theta, hf_theta=hf_theta)
@@ -118,14 +154,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_mc_sample(wl, args, n_points, threads_note):
-    """CPU baseline: the oracle's vectorised predict_mc on a bounded sample of the same workload.
-    Returns (samples_per_s, seconds, description).  Factorisations are setup (untimed), as on the GPU."""
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference itself -- GPy 1.9.9 -- cannot be installed offline)
+# ---------------------------------------------------------------------------------------------------
+def oracle_model(wl):
     from oracle import mfgp_oracle as mo
     o = mo.OracleMFGP(4, 0, 0, hf_4d, lf_X=wl["Xl"], lf_Y=wl["yl"], lf_theta=wl["lf_theta"])
     o.fit(wl["Xh"], theta=wl["hf_theta"])
     o.lf_model.posterior()
     o.hf_model.posterior()
+    return o
+
+
+def oracle_mc_sample(wl, args, n_points, threads_note, o=None):
+    """CPU baseline: the oracle's vectorised predict_mc on a bounded sample of the same workload.
+    Returns (samples_per_s, seconds, description).  Factorisations are setup (untimed), as on the GPU."""
+    o = oracle_model(wl) if o is None else o
     rng = np.random.default_rng(2)
     chunk = 128
     t0 = time.perf_counter()
@@ -142,40 +186,51 @@ def oracle_mc_sample(wl, args, n_points, threads_note):
 
 def run_reference(args):
     """--impl reference: the reference's CPU path for this metric.  The reference itself (GPy) cannot be
-    installed here, so this is the oracle port on all host cores; each step = a bounded sample."""
+    installed here, so this is the oracle port on all host cores; each step = a bounded sample.  Under
+    torchrun only rank 0 works; OMP/OpenBLAS thread counts are forced back to all cores at import time
+    (top of this file) and the count reported is the one the BLAS really runs with."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = workload(args)
-    cores = os.cpu_count()
-    note = "NumPy/SciPy OpenBLAS, %d host threads" % cores
+    wl = workload(args.nh, args.nl, args.m)
+    cores = blas_threads()
+    note = "NumPy/SciPy OpenBLAS, %d BLAS threads (of %d host cpus)" % (cores, os.cpu_count() or 0)
     n_pts = args.ref_points
+    o = oracle_model(wl)
     for _ in range(args.warmup):
-        oracle_mc_sample(wl, args, min(n_pts, 128), note)
-    vals, secs = [], []
+        oracle_mc_sample(wl, args, min(n_pts, 128), note, o)
+    secs = []
     for _ in range(args.steps):
-        v, dt, sample = oracle_mc_sample(wl, args, n_pts, note)
-        vals.append(v); secs.append(dt)
+        v, dt, sample = oracle_mc_sample(wl, args, n_pts, note, o)
+        secs.append(dt)
     value = float(n_pts * args.s * args.steps / sum(secs))
     line = {
         "impl": "reference", "metric": "mc_predictive_samples_per_s", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * sum(secs) / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * sum(secs) / args.steps, "higher_is_better": True, "scaling": scaling_label(args),
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args),
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(), "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference (GPy 1.9.9) not installable offline; oracle port timed on host cores",
+        "note": "reference (GPy 1.9.9) not installable offline; oracle port timed on host cores; one CPU process "
+                "whatever --gpus says (the CPU path does not shard), so only the N=1 ratio is a speed-up",
     }
     print(json.dumps(line))
 
 
+def scaling_label(args):
+    return args.scaling or "strong"
+
+
 def config_dict(args):
+    mode = scaling_label(args)
     return {"workload": "NARGP 2-level MC prediction: M=%d test points (32^4 Gauss-Legendre nodes) x S=%d "
                         "LF posterior samples -> PCE mean; N_h=%d, N_l=%d, d=4 (BASELINE configs[4])"
                         % (args.m, args.s, args.nh, args.nl),
             "M": args.m, "S": args.s, "N_h": args.nh, "N_l": args.nl, "d": 4,
-            "parallelism": "test points sharded, %d rank(s), weak" % args.gpus,
+            "parallelism": ("the SAME M test points split contiguously over %d rank(s) (strong)" % args.gpus)
+            if mode == "strong" else ("every one of %d rank(s) owns its own batch of M points (weak)" % args.gpus),
             "l2": "inputs_larger_than_L2 (cross-covariance chunks of >300 MB stream through HBM each step)"}
 
 
@@ -194,8 +249,10 @@ def measure_fp64_peak(torch):
     return 2.0 * n ** 3 / best / 1e9
 
 
-def lml_grad_section(torch, pkg_ops, peaks, fp64_peak, n=16384):
-    """Secondary metric: LML+gradient evaluations/s at N = 16384 on one B200 (config 4)."""
+# ---------------------------------------------------------------------------------------------------
+# secondary metric: LML + gradient at N = 16384 (config 4), with the oracle at FULL size beside it
+# ---------------------------------------------------------------------------------------------------
+def lml_grad_section(torch, pkg_ops, peaks, fp64_peak, n=16384, cpu=True):
     from multifidelity_datafusion_gps_b200 import _ffi
     rng = np.random.default_rng(1)
     X = rng.uniform(size=(n, 4))
@@ -220,6 +277,11 @@ def lml_grad_section(torch, pkg_ops, peaks, fp64_peak, n=16384):
     hbm = peaks.get("hbm_gbs", 6650.0)
     asm_bytes = 4.0 * n * (n + 1) + 8.0 * n * 5          # lower triangle written + inputs read
     grad_bytes = 4.0 * n * (n + 1) + 8.0 * n * 5         # lower triangle of K^-1 read + inputs
+    # FP64-pipe view of the two covariance kernels: FP64 instructions per element x
+    # lower-triangle elements, against the DFMA rate measured by tools/pipe_probe.cu
+    # (profiles/r01_probe_dfma_dmma_pipe.json: 32.3 TF/s = 16.15 T FP64 instr/s)
+    dfma_instr = 16.15e12
+    tri = 0.5 * n * (n + 1)
     out = {
         "n": n, "evals_per_s": 1e3 / ms_eval, "ms_per_eval": ms_eval, "lml": lml, "info": int(info),
         "stages_ms": {k: float(v) for k, v in zip(names, stages)},
@@ -230,36 +292,280 @@ def lml_grad_section(torch, pkg_ops, peaks, fp64_peak, n=16384):
                            "unit": "TFLOP/s", "frac": n ** 3 / 3 / stages[1] / 1e9 / fp64_peak},
         "roofline_assemble": {"bound": "hbm", "achieved": asm_bytes / stages[0] / 1e6, "peak": hbm,
                               "unit": "GB/s", "frac": asm_bytes / stages[0] / 1e6 / hbm,
-                              "bytes": asm_bytes, "note": "lower triangle only: 4N(N+1)+8ND"},
+                              "bytes": asm_bytes, "note": "lower triangle only: 4N(N+1)+8ND",
+                              "fp64_pipe": {"instr_per_element": 30, "achieved_instr_per_s": 30 * tri / (stages[0] * 1e-3),
+                                            "peak_instr_per_s": dfma_instr,
+                                            "frac": 30 * tri / (stages[0] * 1e-3) / dfma_instr,
+                                            "note": "the binding unit (ncu: fp64 pipe > dram); peak = measured DFMA issue rate"}},
         "roofline_grad_reduce": {"bound": "hbm", "achieved": grad_bytes / stages[5] / 1e6, "peak": hbm,
-                                 "unit": "GB/s", "frac": grad_bytes / stages[5] / 1e6 / hbm},
+                                 "unit": "GB/s", "frac": grad_bytes / stages[5] / 1e6 / hbm,
+                                 "fp64_pipe": {"instr_per_element": 37,
+                                               "frac": 37 * tri / (stages[5] * 1e-3) / dfma_instr}},
         "scaling": "replicas only (single-GPU Cholesky; SURVEY.md section 8e)",
     }
+    alpha = buf.alpha[:n].cpu().numpy()
     del buf, dX, dy
     torch.cuda.empty_cache()
-    # CPU baseline for this metric: the oracle's LML+gradient on the host cores at a
-    # size it finishes in seconds, next to the GPU path at the same size
-    try:
-        from oracle import gpy_oracle as go
-        nc = 4096
-        Xc, yc = Xa[:nc], y[:nc]
-        t0 = time.perf_counter()
-        ref = go.inference(go.KIND_COMPOSITE, Xc, yc, 4, theta)
-        cpu_ms = 1e3 * (time.perf_counter() - t0)
-        dXc, dyc = torch.from_numpy(Xc.copy()).cuda(), torch.from_numpy(yc.ravel().copy()).cuda()
-        bufc = pkg_ops.FactorBuffers(nc, "cuda")
-        pkg_ops.lml_grad(dXc, dyc, _ffi.KIND_COMPOSITE, 4, theta, bufc)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        lml_c, g_c, _ = pkg_ops.lml_grad(dXc, dyc, _ffi.KIND_COMPOSITE, 4, theta, bufc)
-        torch.cuda.synchronize()
-        gpu_ms = 1e3 * (time.perf_counter() - t0)
-        out["cpu_baseline"] = {"n": nc, "cpu_ms_per_eval": cpu_ms, "gpu_ms_per_eval": gpu_ms, "cores": os.cpu_count(),
-                               "kind": "port", "lml_rel_diff": abs(lml_c - ref["lml"]) / abs(ref["lml"]),
-                               "grad_rel_diff": float(np.max(np.abs(g_c - ref["grad"])) / np.max(np.abs(ref["grad"])))}
-    except Exception as exc:      # the baseline is a report, not a dependency of the metric
-        out["cpu_baseline"] = {"error": repr(exc)}
+    if cpu:
+        # CPU baseline for this metric: the oracle's LML+gradient on the host cores at
+        # the FULL size, checked against the GPU result of the same evaluation
+        try:
+            from oracle import gpy_oracle as go
+            t0 = time.perf_counter()
+            ref = go.inference(go.KIND_COMPOSITE, Xa, y, 4, theta)
+            cpu_ms = 1e3 * (time.perf_counter() - t0)
+            out["cpu_baseline"] = {
+                "n": n, "cpu_ms_per_eval": cpu_ms, "gpu_ms_per_eval": ms_eval, "cores": blas_threads(),
+                "kind": "port", "speedup": cpu_ms / ms_eval,
+                "lml_rel_diff": abs(lml - ref["lml"]) / abs(ref["lml"]),
+                "grad_rel_diff": float(np.max(np.abs(g - ref["grad"])) / np.max(np.abs(ref["grad"]))),
+                "alpha_rel_diff": float(np.max(np.abs(alpha - ref["alpha"].ravel())) / np.max(np.abs(ref["alpha"])))}
+            del ref
+        except Exception as exc:      # the baseline is a report, not a dependency of the metric
+            out["cpu_baseline"] = {"error": repr(exc)}
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# acquisition (A9): candidate-set arg-max, candidates resident on the device after the first call
+# ---------------------------------------------------------------------------------------------------
+def small_models(pkg):
+    """The reference's own shapes with N_h = 30 at fixed hyper-parameters (deterministic on every rank):
+    config 2 = GPDF 2-D, tau = 1e-3, two delays (D = 7), 100 000 candidates;
+    config 3 = NARGP 4-D (D = 5), callable lf_4d, 1 048 576 candidates."""
+    rs = np.random.RandomState(10)
+    X2 = rs.uniform(size=(30, 2))
+    m2 = pkg.GPDF(2, 0.001, 2, hf_2d, lf_2d)
+    m2.fit(X2, theta=np.array([1.2, 0.9, 1e-3]))
+    X4 = rs.uniform(size=(30, 4))
+    m3 = pkg.NARGP(4, hf_4d, lf_4d)
+    m3.fit(X4, theta=np.array([1.0, 0.3, 1.0, 0.3, 0.1, 0.3, 1e-3]))
+    c2 = np.random.default_rng(0).uniform(size=(100000, 2))
+    c3 = np.random.default_rng(0).uniform(size=(1 << 20, 4))
+    return {"config2_gpdf_2d_nh30": (m2, c2), "config3_nargp_4d_nh30": (m3, c3)}
+
+
+def time_acquisition(torch, model, cands, distributed, barrier, max_over_ranks, reps=5):
+    """cold = first call (candidate H2D + f_low / LF augmentation + predict + arg-max);
+    resident = later calls (predict + arg-max only)."""
+    model.invalidate_candidate_cache()
+    barrier()
+    t0 = time.perf_counter()
+    idx, val = model.acquisition_argmax(cands, distributed=distributed)
+    torch.cuda.synchronize()
+    cold = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    hits0 = getattr(model, "candidate_cache_hits", 0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        idx2, val2 = model.acquisition_argmax(cands, distributed=distributed)
+    torch.cuda.synchronize()
+    warm = max_over_ranks(1e3 * (time.perf_counter() - t0)) / reps
+    assert (idx2, val2) == (idx, val)
+    C = cands.shape[0]
+    return {"candidates": int(C), "D": int(model.hf_model.D), "N_h": int(model.hf_model.N),
+            "argmax_index": int(idx), "max_variance": float(val),
+            "cold_ms": cold, "resident_ms": warm, "candidates_per_s_cold": C / (cold * 1e-3),
+            "candidates_per_s": C / (warm * 1e-3),
+            "resident_calls_were_cache_hits": bool(model.candidate_cache_hits - hits0 == reps)}
+
+
+def acquisition_section(torch, pkg, model, world, barrier, max_over_ranks, cpu):
+    """N = 1: candidates/s for the three shapes (+ CPU baselines).  N > 1: the same arg-max with the
+    candidates sharded over the ranks; every rank also runs the unsharded arg-max on its own GPU and the
+    block records that the sharded index equals it."""
+    out = {}
+    cases = dict(small_models(pkg))
+    cases["bench_model_nh%d_nl%d" % (model.hf_model.N, model.lf_model.N)] = (
+        model, np.random.default_rng(0).uniform(size=(1 << 20, 4)))
+    for name, (m, cands) in cases.items():
+        single = time_acquisition(torch, m, cands, False, barrier, max_over_ranks)
+        if world > 1:
+            sharded = time_acquisition(torch, m, cands, True, barrier, max_over_ranks)
+            sharded["ranks"] = world
+            sharded["single_gpu_index"] = single["argmax_index"]
+            sharded["index_equals_single_gpu"] = bool(sharded["argmax_index"] == single["argmax_index"]
+                                                      and sharded["max_variance"] == single["max_variance"])
+            sharded["single_gpu_resident_ms"] = single["resident_ms"]
+            out[name] = sharded
+        else:
+            out[name] = single
+    if world == 1 and cpu:
+        from oracle import mfgp_oracle as mo
+        for name, (m, cands) in cases.items():
+            if name.startswith("bench_model"):
+                continue
+            kw = dict(f_low=lf_2d, use_composite_kernel=False) if "config2" in name else dict(f_low=lf_4d)
+            o = mo.OracleMFGP(m.input_dim, m.num_derivatives, m.tau, m.f_exact, **kw)
+            o.fit(m.hf_X, theta=m.hf_model.param_array)
+            t0 = time.perf_counter()
+            i_ref, _, fopt_ref, gap = mo.candidate_argmax(o.predict, cands)
+            dt = time.perf_counter() - t0
+            out[name]["cpu_baseline"] = {"candidates_per_s": cands.shape[0] / dt, "seconds": dt, "kind": "port",
+                                         "cores": blas_threads(), "sample": "all %d candidates" % cands.shape[0],
+                                         "argmax_index": int(i_ref), "index_agrees": bool(i_ref == out[name]["argmax_index"]),
+                                         "top2_rel_gap": gap}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# config-5 sweep: the other (N_h, N_l) points of SURVEY.md section 8d
+# ---------------------------------------------------------------------------------------------------
+def build_model(pkg, gp, wl):
+    model = pkg.NARGP(4, hf_4d, None, lf_X=wl["Xl"][:8], lf_Y=wl["yl"][:8])
+    model.lf_X, model.lf_Y = wl["Xl"], wl["yl"]
+    model.lf_model = gp.GPRegression(wl["Xl"], wl["yl"])
+    model.lf_model._set_params(wl["lf_theta"])
+    model.lf_model._ensure_posterior()
+    model.fit(wl["Xh"], theta=wl["hf_theta"])
+    model.hf_model._ensure_posterior()
+    return model
+
+
+def sweep_section(torch, pkg, gp, fp64_peak, S):
+    """(N_h, N_l) = (30, 100): launch / FP64-ALU bound; (16384, 65536): the config where multi-GPU pays --
+    M reduced to ONE wave of 128-column tiles on 148 SMs (18 944 points) so that it fits a bench slot."""
+    out = []
+    for nh, nl, m, steps in ((30, 100, 32 ** 4, 3), (16384, 65536, 148 * 128, 1)):
+        torch.cuda.synchronize()
+        gp.release_workspaces()
+        torch.cuda.empty_cache()
+        wl = workload(nh, nl, m)
+        t0 = time.perf_counter()
+        model = build_model(pkg, gp, wl)
+        torch.cuda.synchronize()
+        fit_s = time.perf_counter() - t0
+        dX, dw = gp.to_device(wl["Xt"], model.device), gp.to_device(wl["w"], model.device)
+        model.predict_mc_device(dX[:256], S, None, 2, 0, dw[:256])            # pages the kernels in
+        torch.cuda.synchronize()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        for _ in range(steps):
+            mean, var, wsum = model.predict_mc_device(dX, S, None, 2, 0, dw)
+        e_ev.record(); torch.cuda.synchronize()
+        ms = s_ev.elapsed_time(e_ev) / steps
+        flops = float(m) * (nl ** 2 + 2.0 * nl) + float(m) * S * (nh ** 2 + 2.0 * nh)
+        exps = float(m) * nl + float(m) * (2 + S) * nh
+        out.append({"N_h": nh, "N_l": nl, "M": m, "S": S, "steps": steps, "ms_per_step": ms,
+                    "samples_per_s": m * S / (ms * 1e-3), "setup_factorise_both_levels_s": fit_s,
+                    "pce_mean": wsum, "finite": bool(torch.isfinite(mean).all() and torch.isfinite(var).all()),
+                    "roofline": {"bound": "tensor" if nh >= 256 else "fp64 alu / launch",
+                                 "achieved": flops / (ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                                 "frac": flops / (ms * 1e-3) / 1e12 / fp64_peak, "algorithmic_flops": flops,
+                                 "exps": exps, "exps_per_s": exps / (ms * 1e-3),
+                                 "note": "algorithmic flops M(N_l^2+2N_l) + M S (N_h^2+2N_h) (SURVEY.md 8d); the "
+                                         "kernels work on 128-padded factors, so at N_h = 30 the executed "
+                                         "flops are (128/30)^2 times the algorithmic ones"}})
+        del model, dX, dw, mean, var
+    gp.release_workspaces()
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# fit / adapt at the reference's own sizes (configs 1-3), end to end, next to the oracle
+# ---------------------------------------------------------------------------------------------------
+def fit_adapt_section(torch, pkg, cpu):
+    """Config 2 (tests/test_mfgp_adapt_2d.py:27, tests/utils.py:30-35): GPDF 2-D, tau = 1e-3, two delays,
+    5 HF points, 5 adaptation steps over 100 000 candidates (refit after every step); plus one full fit
+    (ARD recipe: 1 + 6 L-BFGS-B runs) at N_h = 30."""
+    from oracle import mfgp_oracle as mo
+    rs = np.random.RandomState(10)
+    rs.uniform(size=(100, 2))
+    X_hf = rs.uniform(size=(5, 2))
+    cands = np.random.default_rng(0).uniform(size=(100000, 2))
+    out = {}
+
+    def gpu_run():
+        np.random.seed(0)
+        m = pkg.GPDF(2, 0.001, 2, hf_2d, lf_2d, adapt_maximizer=pkg.CandidateSetMaximizer(candidates=cands))
+        t0 = time.perf_counter()
+        m.fit(X_hf)
+        t1 = time.perf_counter()
+        m.adapt(5, eps=0.0)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        return m, t1 - t0, t2 - t1
+    gpu_run()                                                       # warm (kernel images, caches)
+    m, fit_s, adapt_s = gpu_run()
+    out["config2_adapt"] = {"fit_s": fit_s, "adapt5_s": adapt_s, "total_s": fit_s + adapt_s,
+                            "lml_evaluations": int(m.hf_model.n_evals), "final_N_h": int(m.hf_model.N),
+                            "final_lml": float(m.hf_model.log_likelihood())}
+    X30 = np.random.RandomState(11).uniform(size=(30, 2))
+
+    def gpu_fit30():
+        np.random.seed(1)
+        m = pkg.GPDF(2, 0.001, 2, hf_2d, lf_2d)
+        t0 = time.perf_counter()
+        m.fit(X30)
+        torch.cuda.synchronize()
+        return m, time.perf_counter() - t0
+    gpu_fit30()
+    m30, fit30_s = gpu_fit30()
+    out["fit_nh30"] = {"fit_s": fit30_s, "lml": float(m30.hf_model.log_likelihood()),
+                       "lml_evaluations_last_run": int(m30.hf_model.n_evals)}
+    # one adaptation step under the reference's DEFAULT maximizer (DIRECT: 20 000 sequential one-row predicts)
+    md = pkg.GPDF(2, 0.001, 2, hf_2d, lf_2d)
+    md.fit(X30, theta=m30.hf_model.param_array)
+    t0 = time.perf_counter()
+    x_d, f_d = md.get_input_with_highest_uncertainty(md)
+    direct_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    i_c, v_c = md.acquisition_argmax(cands)
+    cand_s = time.perf_counter() - t0
+    out["direct_vs_candidates_nh30"] = {"direct_20000_single_point_predicts_s": direct_s, "direct_fopt": float(f_d),
+                                        "candidate_argmax_100k_s_cold": cand_s, "candidate_fopt": -float(v_c),
+                                        "note": "scipy.optimize.direct stands in for scipydirect (same settings)"}
+    if cpu:
+        def cpu_run():
+            o = mo.OracleMFGP(2, 2, 0.001, hf_2d, f_low=lf_2d, use_composite_kernel=False,
+                              rng=np.random.RandomState(0))
+            t0 = time.perf_counter()
+            o.fit(X_hf)
+            t1 = time.perf_counter()
+            o.adapt(5, mo.make_candidate_maximizer(cands), eps=0.0)
+            t2 = time.perf_counter()
+            return o, t1 - t0, t2 - t1
+        o, cfit, cadapt = cpu_run()
+        out["config2_adapt"]["cpu_baseline"] = {"fit_s": cfit, "adapt5_s": cadapt, "total_s": cfit + cadapt,
+                                                "kind": "port", "cores": blas_threads(),
+                                                "final_lml": float(o.hf_model.log_likelihood())}
+        out["config2_adapt"]["speedup_total"] = (cfit + cadapt) / (fit_s + adapt_s)
+        o30 = mo.OracleMFGP(2, 2, 0.001, hf_2d, f_low=lf_2d, use_composite_kernel=False,
+                            rng=np.random.RandomState(1))
+        t0 = time.perf_counter()
+        o30.fit(X30)
+        c30 = time.perf_counter() - t0
+        out["fit_nh30"]["cpu_baseline"] = {"fit_s": c30, "lml": float(o30.hf_model.log_likelihood()),
+                                           "kind": "port", "cores": blas_threads()}
+        out["fit_nh30"]["speedup"] = c30 / fit30_s
+        # DIRECT-style search on the CPU: the same 20 000 sequential single-point predicts over the oracle
+        from scipy.optimize import direct
+        o30.fit(X30, theta=m30.hf_model.param_array)
+        t0 = time.perf_counter()
+        res = direct(lambda x: -float(o30.predict(np.asarray(x)[None])[1][0, 0]), [(0.0, 1.0)] * 2, eps=1e-4,
+                     maxfun=20000, maxiter=6000, locally_biased=False, vol_tol=0.0, len_tol=0.0)
+        out["direct_vs_candidates_nh30"]["cpu_direct_s"] = time.perf_counter() - t0
+        out["direct_vs_candidates_nh30"]["cpu_direct_fopt"] = float(res.fun)
+    return out
+
+
+def per_row_reference_loop(wl, n_rows):
+    """'As the reference does it' (src/MFDataFusion.py:193-197): f_low = lf_model.predict(.)[0] called once
+    PER ROW by a Python map, then one HF predict.  Timed on the first n_rows test points."""
+    o = oracle_model(wl)
+    X = wl["Xt"][:n_rows]
+    t0 = time.perf_counter()
+    vals = np.array([o.f_low(x[None, :])[0] for x in X]).reshape(n_rows, 1)
+    Xa = np.concatenate([X, vals], axis=1)
+    mean, var = o.hf_model.predict(Xa)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    mean_v, var_v = o.predict(X)
+    dt_vec = time.perf_counter() - t0
+    return {"rows": n_rows, "seconds": dt, "points_per_s": n_rows / dt, "vectorised_port_points_per_s": n_rows / dt_vec,
+            "kind": "port", "cores": blas_threads(),
+            "max_abs_diff_vs_vectorised": float(np.max(np.abs(mean - mean_v)))}
 
 
 def main():
@@ -268,6 +574,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default=None)
     ap.add_argument("--nh", type=int, default=1024)
     ap.add_argument("--nl", type=int, default=4096)
     # (--points / --samples rather than --m / --s: torchrun's own parser treats "--m" as ambiguous)
@@ -277,6 +584,7 @@ def main():
     ap.add_argument("--cpu-points", type=int, default=1024, dest="cpu_points")
     ap.add_argument("--no-lml", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only (profiling runs)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -294,16 +602,18 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         tdist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = "cuda:%d" % local
+    args.gpus = world
+    strong = scaling_label(args) == "strong"
 
     import multifidelity_datafusion_gps_b200 as pkg
-    from multifidelity_datafusion_gps_b200 import _ffi, gp, ops
+    from multifidelity_datafusion_gps_b200 import _ffi, dist, gp, ops
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
 
-    wl = workload(args)
+    wl = workload(args.nh, args.nl, args.m)
     # ---- setup (untimed): fit state on rank 0 at fixed theta, NCCL broadcast of the factorised state
     # The constructor trains the LF GP with L-BFGS-B (reference src/abstractMFGP.py:100-103); the bench
     # runs at FIXED hyper-parameters, so it is built on an 8-point stub and the real LF level is
@@ -328,35 +638,12 @@ def main():
         bcast_ms = 1e3 * (time.perf_counter() - t0)
 
     M, S = args.m, args.s
-    m0 = rank * M                                   # weak scaling: every rank owns its own batch
-    Xt_pin = torch.from_numpy(wl["Xt"]).pin_memory()
-    w_pin = torch.from_numpy(wl["w"]).pin_memory()
-    dX = Xt_pin.to(dev)
-    dw = w_pin.to(dev)
     h = _ffi.get_handle(local)
 
     def barrier():
         if world > 1:
             tdist.barrier()
         torch.cuda.synchronize()
-
-    def step_device():
-        mean, var, wsum = model.predict_mc_device(dX, S, None, 2, m0, dw)
-        if world > 1:
-            t = torch.tensor([wsum], dtype=torch.float64, device=dev)
-            tdist.all_reduce(t)
-            wsum = float(t.item())
-        return wsum
-
-    def step_e2e():
-        # public API, host buffers: pinned NumPy views in, NumPy out (H2D + D2H inside the timed region)
-        mean, var = model.predict_mc(Xt_pin.numpy(), n_samples=S, seed=2, weights=w_pin.numpy(), m0=m0)
-        wsum = model.last_pce_mean
-        if world > 1:
-            t = torch.tensor([wsum], dtype=torch.float64, device=dev)
-            tdist.all_reduce(t)
-            wsum = float(t.item())
-        return wsum, mean, var
 
     def max_over_ranks(ms):
         if world == 1:
@@ -365,120 +652,148 @@ def main():
         tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
-        pce = step_device()
-    # ---- timed: device-resident inputs
-    sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
-    if sampler:
-        sampler.start()
-    h.profile_enable(True)
-    launches0 = h.launches
-    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s_ev.record()
-    for _ in range(args.steps):
-        pce = step_device()
-    e_ev.record()
-    barrier()
-    launches = h.launches - launches0
-    prof = h.profile_read()
-    h.profile_enable(False)
-    ms_dev = max_over_ranks(s_ev.elapsed_time(e_ev)) / args.steps
-    clocks = sampler.stop() if sampler else None
+    def run_mode(strong_mode, steps, warmup, with_e2e, sample_clocks):
+        """One timed experiment: `steps` device-resident steps (value), then `steps` end-to-end steps."""
+        lo, hi = dist.shard_range(M, rank, world) if strong_mode else (0, M)
+        m0 = lo if strong_mode else rank * M          # global index of this rank's first point (keys Philox)
+        Xt_pin = torch.from_numpy(wl["Xt"][lo:hi]).pin_memory()
+        w_pin = torch.from_numpy(wl["w"][lo:hi]).pin_memory()
+        dX, dw = Xt_pin.to(dev), w_pin.to(dev)
 
-    # ---- timed: end to end through the public API with host buffers
-    step_e2e()
-    barrier()
-    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    s_ev.record()
-    for _ in range(args.steps):
-        pce_e2e, mean_h, var_h = step_e2e()
-    e_ev.record()
-    barrier()
-    ms_e2e = max_over_ranks(max(s_ev.elapsed_time(e_ev), 1e3 * (time.perf_counter() - t0))) / args.steps
-    h2d = wl["Xt"].nbytes + wl["w"].nbytes
-    d2h = mean_h.nbytes + var_h.nbytes + 8
+        def reduce_pce(wsum):
+            if world > 1:
+                t = torch.tensor([wsum], dtype=torch.float64, device=dev)
+                tdist.all_reduce(t)
+                wsum = float(t.item())
+            return wsum
 
-    total_samples = float(world) * M * S
-    value = total_samples / (ms_dev * 1e-3)
-    e2e_value = total_samples / (ms_e2e * 1e-3)
+        def step_device():
+            mean, var, wsum = model.predict_mc_device(dX, S, None, 2, m0, dw)
+            return reduce_pce(wsum)
+
+        def step_e2e():
+            # public API, host buffers: pinned NumPy views in, NumPy out (H2D + D2H inside the timed region)
+            mean, var = model.predict_mc(Xt_pin.numpy(), n_samples=S, seed=2, weights=w_pin.numpy(), m0=m0)
+            return reduce_pce(model.last_pce_mean), mean, var
+
+        for _ in range(warmup):
+            pce = step_device()
+        sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
+        barrier()
+        if sampler:
+            sampler.start()
+        h.profile_enable(True)
+        launches0 = h.launches
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        for _ in range(steps):
+            pce = step_device()
+        e_ev.record()
+        barrier()
+        launches = h.launches - launches0
+        prof = h.profile_read()
+        h.profile_enable(False)
+        ms_dev = max_over_ranks(s_ev.elapsed_time(e_ev)) / steps
+        clocks = sampler.stop() if sampler else None
+        total = float(M) * S * (1 if strong_mode else world)
+        res = {"ms_dev": ms_dev, "value": total / (ms_dev * 1e-3), "pce": pce, "launches": launches, "prof": prof,
+               "clocks": clocks, "points_per_rank": hi - lo, "total_samples": total}
+        if with_e2e:
+            step_e2e()
+            barrier()
+            s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            s_ev.record()
+            for _ in range(steps):
+                pce_e2e, mean_h, var_h = step_e2e()
+            e_ev.record()
+            barrier()
+            ms_e2e = max_over_ranks(max(s_ev.elapsed_time(e_ev), 1e3 * (time.perf_counter() - t0))) / steps
+            res.update(ms_e2e=ms_e2e, e2e_value=total / (ms_e2e * 1e-3), pce_e2e=pce_e2e,
+                       h2d=int((Xt_pin.numel() + w_pin.numel()) * 8), d2h=int(mean_h.nbytes + var_h.nbytes + 8))
+        del dX, dw
+        return res
+
+    main_res = run_mode(strong, args.steps, args.warmup, True, True)
+    weak_res = None
+    if world > 1 and strong and not args.no_extras:
+        weak_res = run_mode(False, 2, 1, False, False)       # secondary: every rank its own M points
+
+    acq = None
+    if not args.no_extras:
+        acq = acquisition_section(torch, pkg, model, world, barrier, max_over_ranks, cpu=not args.no_cpu)
 
     if rank == 0:
         fp64_peak = measure_fp64_peak(torch)
+        prof = main_res["prof"]
+        ms_dev = main_res["ms_dev"]
         trmm_ms, trmm_cnt = prof["trmm_sumsq"]
         hf_launches_per_step = max(trmm_cnt / args.steps, 1.0)
-        cols_per_launch = M * S / hf_launches_per_step
+        cols_per_launch = main_res["points_per_rank"] * S / hf_launches_per_step
         flops_per_launch = cols_per_launch * float(args.nh) ** 2       # N_h^2 per (point, sample)
         achieved = flops_per_launch / (trmm_ms * 1e-3) / 1e12 if trmm_ms > 0 else 0.0
         roofline = {"bound": "tensor", "kernel": "dg::trmm_sumsq_kernel (tmp = W Kx, fused column sum of squares)",
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp64_peak if fp64_peak else None,
-                    # DRAM read+write per launch from the ncu --set full capture of this kernel
-                    # (profiles/r01_ncu_mc_hf_kernels_v6.txt: 1.651 GB for 75 776 columns at N_h = 1024),
-                    # scaled to this run's columns per launch
-                    "traffic": (1.651e9 / 75776.0 * cols_per_launch) if args.nh == 1024 else None,
+                    "traffic": traffic_per_launch(args.nh, cols_per_launch),
                     "avg_launch_ms": trmm_ms, "launches_per_step": hf_launches_per_step,
                     "flops_per_launch": flops_per_launch,
+                    "timing": "CUDA event pairs on the launching stream around every launch of the class inside the "
+                              "timed region; the average is over the first 512 launches per class (mfgp_profile_*)",
                     "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no FP64 "
                                    "figure; tcgen05 has no FP64 kind, FP64 MMA on sm_100a is DMMA.8x8x4)",
                     "share_of_step": trmm_ms * hf_launches_per_step / ms_dev,
                     "other_kernels_ms_per_launch": {k: v[0] for k, v in prof.items() if v[1] > 0}}
         line = {
-            "metric": "mc_predictive_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args),
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "pce_mean": pce, "pce_mean_e2e": pce_e2e,
+            "metric": "mc_predictive_samples_per_s", "value": main_res["value"], "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+            "higher_is_better": True, "scaling": scaling_label(args), "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args),
+            "e2e": {"value": main_res["e2e_value"], "unit": "samples/s", "h2d_bytes_per_step": main_res["h2d"],
+                    "d2h_bytes_per_step": main_res["d2h"], "ms_per_step": main_res["ms_e2e"],
+                    "note": "public NumPy API; bytes are per rank; the host arrays are pinned by bench.py -- a "
+                            "pageable array takes gp.to_device's pin_memory() staging copy first (+~10 ms per "
+                            "40 MB, immaterial at this step length)"},
+            "gpu_launches": int(main_res["launches"]), "clocks": main_res["clocks"], "roofline": roofline,
+            "pce_mean": main_res["pce"], "pce_mean_e2e": main_res["pce_e2e"],
+            "points_per_rank": int(main_res["points_per_rank"]),
             "setup": {"fit_fixed_theta_s": fit_s, "nccl_broadcast_state_ms": bcast_ms},
         }
-        if not args.no_cpu:
-            v, dt, sample = oracle_mc_sample(wl, args, args.cpu_points,
-                                             "NumPy/SciPy OpenBLAS, %d host threads" % os.cpu_count())
-            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+        if weak_res is not None:
+            line["weak"] = {"value": weak_res["value"], "ms_per_step": weak_res["ms_dev"], "steps": 2,
+                            "note": "secondary: every rank its own batch of M points"}
+        if acq is not None:
+            line["acquisition_sharded" if world > 1 else "acquisition"] = acq
+        if world == 1 and not args.no_cpu:
+            cores = blas_threads()
+            v, dt, sample = oracle_mc_sample(wl, args, args.cpu_points, "NumPy/SciPy OpenBLAS, %d BLAS threads" % cores)
+            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": sample, "seconds": dt}
-        if world == 1 and not args.no_lml:
-            # acquisition throughput (candidates/s for A9): arg-max of the predictive
-            # variance over the same M points taken as candidates, device-resident
-            acq_ms = []
-            for i in range(3):
-                s_a, e_a = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s_a.record()
-                _, var_c = model._predict_device(dX)
-                c_val, c_idx = ops.argmax(var_c)
-                e_a.record(); torch.cuda.synchronize()
-                if i > 0:
-                    acq_ms.append(s_a.elapsed_time(e_a))
-            line["acquisition"] = {"candidates": int(M), "N_h": args.nh, "N_l": args.nl,
-                                   "ms": float(np.mean(acq_ms)),
-                                   "candidates_per_s": float(M / (np.mean(acq_ms) * 1e-3)),
-                                   "argmax_index": int(c_idx), "max_variance": float(c_val)}
-            if not args.no_cpu:
-                # CPU baseline: the oracle's vectorised predict + np.argmax on a bounded sample of the candidates
-                from oracle import mfgp_oracle as mo
-                o = mo.OracleMFGP(4, 0, 0, hf_4d, lf_X=wl["Xl"], lf_Y=wl["yl"], lf_theta=wl["lf_theta"])
-                o.fit(wl["Xh"], theta=wl["hf_theta"])
-                o.lf_model.posterior(); o.hf_model.posterior()
-                nc = 8192
-                t0 = time.perf_counter()
-                v_ref = o.predict(wl["Xt"][M - nc:])[1].ravel()
-                i_ref = int(np.argmax(v_ref))
-                dt = time.perf_counter() - t0
-                line["acquisition"]["cpu_baseline"] = {
-                    "candidates_per_s": nc / dt, "cores": os.cpu_count(), "kind": "port",
-                    "sample": "last %d of %d candidates, NumPy/SciPy oracle" % (nc, M), "seconds": dt,
-                    "argmax_agrees_on_sample": bool(M - nc + i_ref == int(c_idx)) if int(c_idx) >= M - nc else None}
-            del dX
-            gp._ws_pool.clear()
+            if not args.no_extras:
+                line["cpu_baseline"]["per_row_reference_loop"] = per_row_reference_loop(wl, 1024)
+        if world == 1 and not args.no_extras:
+            del model
+            gp.release_workspaces()
             torch.cuda.empty_cache()
-            line["lml_grad"] = lml_grad_section(torch, ops, peaks, fp64_peak)
+            line["fit_adapt"] = fit_adapt_section(torch, pkg, cpu=not args.no_cpu)
+            line["sweep"] = sweep_section(torch, pkg, gp, fp64_peak, S)
+            if not args.no_lml:
+                line["lml_grad"] = lml_grad_section(torch, ops, peaks, fp64_peak, cpu=not args.no_cpu)
         print(json.dumps(line))
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
+
+
+def traffic_per_launch(nh, cols_per_launch):
+    """DRAM read+write per trmm_sumsq launch from the ncu --set full capture of this kernel, scaled to this
+    run's columns per launch (profiles/: bytes per column at N_h = 1024); None for other sizes."""
+    per_col = TRAFFIC_BYTES_PER_COLUMN.get(nh)
+    return per_col * cols_per_launch if per_col else None
+
+
+# profiles/r01_ncu_mc_hf_kernels_v6.txt: 1.651 GB for 75 776 columns at N_h = 1024
+TRAFFIC_BYTES_PER_COLUMN = {1024: 1.651e9 / 75776.0}
 
 
 if __name__ == "__main__":

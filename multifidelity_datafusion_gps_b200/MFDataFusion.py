@@ -16,6 +16,7 @@ Extensions (keyword-only, defaults reproduce the reference):
 * ``broadcast_state``  NCCL broadcast of the fitted state so that other ranks can predict.
 """
 import ctypes
+import zlib
 
 import numpy as np
 import torch
@@ -106,7 +107,8 @@ class MultifidelityDataFusion(AbstractMFGP):
         """(mean (M,1), variance (M,1)); the variance includes the noise variance (GPy semantics)."""
         assert X_test.ndim == 2
         assert X_test.shape[1] == self.input_dim
-        mean, var = self._predict_device(gp.to_device(X_test, self.device))
+        self._apply_add_noise()
+        mean, var = self.hf_model.predict_device(self._augment_host_input(X_test), True, True)
         return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]
 
     def _apply_add_noise(self):
@@ -128,18 +130,44 @@ class MultifidelityDataFusion(AbstractMFGP):
 
     # -- A1 augmentation --------------------------------------------------------------------------
     def _f_low_batched(self, locations):
-        """Host callable f_low on (rows, d) locations -> (rows,).  One vectorised call; if the
-        callable is not row-vectorised, fall back to the reference's per-group calls (:197)."""
+        """Host callable f_low on (M, E, d) locations -> (M, E).  The reference calls f_low once per
+        (E, d) group (:197).  Whether the callable is also row-wise on a stack of groups is probed ONCE
+        per callable -- the first group through the reference's call, then the first two groups stacked,
+        which must return one value per row and reproduce the first group -- and cached; genuine errors
+        of f_low propagate from the reference-style call instead of being swallowed."""
         M, E = locations.shape[0], locations.shape[1]
+        if M == 0:
+            return np.zeros((0, E))
         flat = locations.reshape(M * E, self.input_dim)
-        try:
+        mode = getattr(self, "_f_low_mode", None)
+        if mode is None or mode[0] is not self.f_low:
+            first = np.asarray(self.f_low(locations[0]), dtype=np.float64)       # errors surface here, as in :197
+            assert first.size == E, "f_low must return one value per row"
+            n = min(M, 2) * E
+            rowwise = False
+            try:
+                probe = np.asarray(self.f_low(flat[:n]), dtype=np.float64)
+                rowwise = probe.shape in ((n,), (n, 1)) and np.allclose(probe.ravel()[:E], first.ravel(),
+                                                                        rtol=1e-12, atol=0.0)
+            except (ValueError, IndexError):      # shape-related only: not vectorised over stacked groups
+                rowwise = False
+            mode = self._f_low_mode = (self.f_low, rowwise)
+        if mode[1]:
             vals = np.asarray(self.f_low(flat), dtype=np.float64)
-            if vals.size == M * E:
-                return vals.reshape(M, E)
-        except Exception:
-            pass
-        vals = np.array([np.asarray(self.f_low(loc), dtype=np.float64).reshape(E) for loc in locations])
-        return vals
+            assert vals.shape in ((M * E,), (M * E, 1)), "f_low must return one value per row"
+            return vals.reshape(M, E)
+        return np.array([np.asarray(self.f_low(loc), dtype=np.float64).reshape(E) for loc in locations])
+
+    def _augment_host_input(self, X):
+        """Host (M, d) inputs -> (M, d+E) CUDA tensor.  A callable low fidelity is evaluated on the host
+        array it arrived as and the augmented rows go up in ONE copy (no device round trip); a data-driven
+        or device-evaluable low fidelity augments on the GPU."""
+        if self.data_driven_lf_approach or getattr(self.f_low, "device_predict", None) is not None:
+            return self._augment_device(gp.to_device(X, self.device))
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        offsets = self.augm_iterator.offset_table()
+        locations = X[:, None, :] + offsets[None, :, :] * self.tau
+        return gp.to_device(np.concatenate([X, self._f_low_batched(locations)], axis=1), self.device)
 
     def _augment_device(self, dX):
         """(M, d) CUDA tensor -> (M, d+E) CUDA tensor."""
@@ -165,16 +193,15 @@ class MultifidelityDataFusion(AbstractMFGP):
             loc = (dX[:, None, :] + offs[None, :, :]).reshape(M * E, self.input_dim).contiguous()
             vals = dev_f(loc).reshape(M, E)
             return torch.cat([dX, vals], dim=1).contiguous()
-        X = dX.cpu().numpy()
-        locations = X[:, None, :] + offsets[None, :, :] * self.tau
-        Xa = np.concatenate([X, self._f_low_batched(locations)], axis=1)
-        return gp.to_device(Xa, self.device)
+        # host callable on device-resident inputs (bench / gPC hand in CUDA tensors): the rows have to visit
+        # the host, where the callable lives
+        return self._augment_host_input(dX.cpu().numpy())
 
     def __augment_Data(self, X):
         """X (M,d) -> [X, f_low(x + o_0 tau), ..., f_low(x + o_{E-1} tau)]  (M, d+E), NumPy."""
         assert X.shape == (len(X), self.input_dim)
         E = self.augm_iterator.new_entries_count()
-        if self.data_driven_lf_approach:
+        if self.data_driven_lf_approach or getattr(self.f_low, "device_predict", None) is not None:
             Xa = self._augment_device(gp.to_device(X, self.device)).cpu().numpy()
         else:
             offsets = self.augm_iterator.offset_table()
@@ -208,7 +235,7 @@ class MultifidelityDataFusion(AbstractMFGP):
                 per_col = (nph + d + 3) * 8
                 want = 16 * M + 148 * 128 * 4 * per_col
                 need = 16 * M + max((S + 256) * per_col, (npl + 1) * 128 * 8) + 4096
-                ws_bytes = max(min(want, 2 << 30), need)
+                ws_bytes = max(min(want, 12 << 30), need)     # ~4 column tiles per SM up to N_h = 16384
             ws = gp.workspace(self.device, ws_bytes)
             h.check(h.lib.mfgp_predict_mc(
                 h.h, ctypes.byref(lf), ctypes.byref(hf), dX.data_ptr(), M, S,
@@ -260,17 +287,48 @@ class MultifidelityDataFusion(AbstractMFGP):
         return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]
 
     # -- A9 acquisition (extension) ------------------------------------------------------------------
-    def acquisition_argmax(self, candidates, distributed=False):
+    def _lf_state_key(self):
+        """Identity of the low-fidelity level as the augmentation sees it: changes when the LF model is
+        replaced, refitted, or its data / hyper-parameters change (gp.GPRegression._version)."""
+        if self.data_driven_lf_approach:
+            return ("gp", id(self.lf_model), self.lf_model._version)
+        return ("callable", id(self.f_low))
+
+    def invalidate_candidate_cache(self):
+        self._cand_cache = None
+
+    def _resident_candidates(self, candidates, lo, hi):
+        """Augmented rows [c, f_low(c + o tau)] of the shard candidates[lo:hi], kept on the device.  The
+        candidate set is fixed during an adaptation run (CandidateSetMaximizer) and the low-fidelity level
+        does not change while high-fidelity points are acquired (src/abstractMFGP.py:317-359), so after the
+        first step an acquisition performs no candidate H2D / D2H and no f_low evaluation.  The cache is
+        keyed on the array (address, shape, a checksum of a strided sample of rows), the shard and the
+        low-fidelity state; ``invalidate_candidate_cache()`` drops it explicitly."""
+        c = np.ascontiguousarray(candidates, dtype=np.float64)
+        step = max(1, c.shape[0] // 4096)
+        key = (c.ctypes.data, c.shape, zlib.crc32(np.ascontiguousarray(c[::step]).tobytes()), lo, hi,
+               float(self.tau), self.augm_iterator.offset_table().tobytes(), self._lf_state_key())
+        cache = getattr(self, "_cand_cache", None)
+        if cache is not None and cache[0] == key:
+            self.candidate_cache_hits = getattr(self, "candidate_cache_hits", 0) + 1
+            return cache[1]
+        dXa = self._augment_host_input(c[lo:hi])
+        self._cand_cache = (key, dXa)
+        return dXa
+
+    def acquisition_argmax(self, candidates, distributed=False, cache=True):
         """(index, variance) of the candidate with the largest predictive variance; lowest index on
         ties.  With distributed=True every rank scores a contiguous shard and the winners are combined
-        with one all_gather (all ranks must hold the same fitted state, see broadcast_state)."""
+        with one all_gather (all ranks must hold the same fitted state, see broadcast_state).
+        cache=True keeps the augmented shard resident on the device between calls (_resident_candidates)."""
         C = candidates.shape[0]
         rank, world = dist.rank_world() if distributed else (0, 1)
         lo, hi = dist.shard_range(C, rank, world)
         val, idx = -np.inf, -1
         if hi > lo:
-            dC = gp.to_device(candidates[lo:hi], self.device)
-            _, var = self._predict_device(dC)
+            dXa = self._resident_candidates(candidates, lo, hi) if cache else self._augment_host_input(candidates[lo:hi])
+            self._apply_add_noise()
+            _, var = self.hf_model.predict_device(dXa, True, True)
             h = _ffi.get_handle(self.device)
             c_val, c_idx = ctypes.c_double(), ctypes.c_longlong()
             h.check(h.lib.mfgp_argmax(h.h, var.data_ptr(), hi - lo, ctypes.byref(c_val), ctypes.byref(c_idx)))
@@ -290,8 +348,11 @@ class MultifidelityDataFusion(AbstractMFGP):
         levels = ["hf_model"] + (["lf_model"] if self.data_driven_lf_approach else [])
         meta = [None]
         if rank == src:
+            for name in levels:
+                getattr(self, name)._ensure_posterior()       # settles last_jitter before it is sent
             meta[0] = {name: dict(X=getattr(self, name).X, Y=getattr(self, name).Y,
-                                  theta=getattr(self, name).param_array) for name in levels}
+                                  theta=getattr(self, name).param_array,
+                                  jitter=getattr(self, name).last_jitter) for name in levels}
             meta[0]["hf_X"] = self.hf_X
             meta[0]["kernel"] = self.kernel.param_array.copy()
         tdist.broadcast_object_list(meta, src=src)
@@ -309,3 +370,8 @@ class MultifidelityDataFusion(AbstractMFGP):
                 model._ensure_posterior()
             dist.broadcast_tensors([model._dW, model._dalpha], src=src)
             model._dirty = False
+            if rank != src:
+                # receivers hold W and alpha only: their A buffer is not L (append_point must not read it),
+                # and a later bordered update has to use the jitter the broadcast factor was built with
+                model.last_jitter = float(m[name]["jitter"])
+                model._a_holds_L = False

@@ -6,6 +6,7 @@ missing, or no B200 is present, the first call raises.
 """
 import ctypes
 import os
+import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MFGP_LIB: kernel-tuning override (tools/build_variants.sh builds A/B variants of the same library)
@@ -161,16 +162,25 @@ class Handle:
 
 
 _handles = {}
+_handles_lock = threading.Lock()
 
 
 def get_handle(device=0):
-    """Process-wide handle per device, bound to torch's current stream on that device."""
+    """One handle per (device, Python thread), bound to torch's current stream on that device.
+    A handle owns its stream binding, result staging and scratch, and ctypes releases the GIL during
+    calls, so two threads must never share one (include/mfgp_b200.h: thread-compatible per handle)."""
     import torch
     if not torch.cuda.is_available():
         raise MfgpError("no CUDA device visible: mfgp_b200 has no CPU fallback")
-    device = int(device)
-    if device not in _handles:
-        _handles[device] = Handle(device)
-    h = _handles[device]
-    h.set_stream(torch.cuda.current_stream(device).cuda_stream)
+    key = (int(device), threading.get_ident())
+    h = _handles.get(key)
+    if h is None:
+        with _handles_lock:
+            h = _handles[key] = Handle(int(device))
+    h.set_stream(torch.cuda.current_stream(int(device)).cuda_stream)
     return h
+
+
+def total_launches(device=None):
+    """Kernels launched by every handle of this process (optionally of one device)."""
+    return sum(h.launches for (dev, _), h in list(_handles.items()) if device is None or dev == int(device))

@@ -1,7 +1,11 @@
 """DIRECT global search over single-point predicts, as the reference's default maximizer does
 (src/adaptation_maximizers/scipydirect_wrapper.py:16-31).  ``scipydirect`` (Fortran DIRECT) is not
-a dependency of this package; ``scipy.optimize.direct`` is used as a stand-in with scipydirect's
-default budget (maxf=20000, maxT=6000, eps=1e-4).  It is kept for drop-in compatibility of the
+a dependency of this package; ``scipy.optimize.direct`` stands in, configured like scipydirect's
+defaults: the ORIGINAL DIRECT (algmethod=0 -> ``locally_biased=False``), budget maxf=20000, maxT=6000,
+eps=1e-4, and the volume / side-length terminations switched off (volper=-1, sigmaper=-1 ->
+``vol_tol=0``, ``len_tol=0``), so that the search normally spends its whole evaluation budget as the
+reference's does.  Remaining deviation: two DIRECT implementations (Gablonsky's Fortran vs. SciPy's C
+port of it) may order equal-sized rectangles differently.  It is kept for drop-in compatibility of the
 default constructor argument; the GPU-native acquisition is ``CandidateSetMaximizer``."""
 import numpy as np
 
@@ -21,5 +25,6 @@ class ScipyDirectMaximizer(AbstractMaximizer):
             _, uncertainty = model_predict(np.asarray(x)[None])
             return -float(np.asarray(uncertainty).ravel()[0])
 
-        res = direct(acquisition_curve, bound, eps=self.eps, maxfun=self.maxf, maxiter=self.maxT)
+        res = direct(acquisition_curve, bound, eps=self.eps, maxfun=self.maxf, maxiter=self.maxT,
+                     locally_biased=False, vol_tol=0.0, len_tol=0.0)
         return res.x, res.fun

@@ -46,11 +46,22 @@ int wdot_launch(mfgp_ctx* h, const double* w, const double* x, long long n, doub
 
 static char g_err[256] = "invalid handle";
 
-#define ENTER(h)                 \
-  do {                           \
-    if (!(h)) return -1;         \
-    cudaSetDevice((h)->device);  \
-  } while (0)
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it
+// (torch's current device must not change under the caller).
+struct DeviceGuard {
+  int prev, dev;
+  bool restore;
+  explicit DeviceGuard(int d) : prev(-1), dev(d), restore(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) restore = true;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (restore) cudaSetDevice(prev);
+  }
+};
+#define ENTER(h)        \
+  if (!(h)) return -1;  \
+  DeviceGuard _device_guard((h)->device)
 
 int make_kparams(mfgp_ctx* h, int kind, int D, int d, const double* theta, int P, KParams* kp) {
   ARG_CHECK(h, theta != nullptr);
@@ -187,7 +198,6 @@ int mfgp_create(int device, mfgp_handle_t* out) {
 
 int mfgp_destroy(mfgp_handle_t h) {
   ENTER(h);
-  cudaSetDevice(h->device);
   cudaFree(h->d_partials);
   cudaFree(h->d_scalars);
   cudaFree(h->d_info);
@@ -511,7 +521,10 @@ int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t*
   if ((rc = level_kparams(h, lf, &kl))) return rc;
   if ((rc = level_kparams(h, hf, &kh))) return rc;
   const int d = lf->D;
-  ARG_CHECK(h, hf->d == d && hf->D == d + 1);   // E = 1 (NARGP) only
+  // E = 1: NARGP (composite kernel on [x, z]) or GPDF without delays (one RBF over [x, z]: az == ax, so
+  // the same code runs with the split at d)
+  ARG_CHECK(h, hf->D == d + 1 && (hf->d == d || hf->kind == MFGP_KIND_RBF));
+  kh.d = d;
   ARG_CHECK(h, lf->d_W && hf->d_W && d_Xtest && d_mean && d_var && d_ws && S >= 1 && M >= 0);
   if (M == 0) return 0;
   const long long wsd = (long long)(ws_bytes / sizeof(double));

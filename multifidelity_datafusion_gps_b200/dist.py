@@ -37,11 +37,19 @@ def combine_argmax(vals, idxs):
     return best_v, best_i
 
 
+def coll_device(device=None):
+    """Where the small collectives stage their tensors: the rank's GPU under NCCL, the host under gloo
+    (gloo has no CUDA all_gather; the CPU tests and the one-GPU two-rank test run on it)."""
+    if device is None or not is_dist() or tdist.get_backend() != "nccl":
+        return "cpu"
+    return device
+
+
 def gather_argmax(local_val, local_idx, device=None):
     """all_gather of one (f64 value, i64 global index) pair per rank, then combine_argmax."""
     if not is_dist():
         return float(local_val), int(local_idx)
-    dev = device if device is not None else "cpu"
+    dev = coll_device(device)
     v = torch.tensor([float(local_val)], dtype=torch.float64, device=dev)
     i = torch.tensor([int(local_idx)], dtype=torch.int64, device=dev)
     world = tdist.get_world_size()
@@ -88,6 +96,6 @@ def broadcast_tensors(tensors, src=0):
 def allreduce_sum_scalar(x, device=None):
     if not is_dist():
         return float(x)
-    t = torch.tensor([float(x)], dtype=torch.float64, device=device if device is not None else "cpu")
+    t = torch.tensor([float(x)], dtype=torch.float64, device=coll_device(device))
     tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
     return float(t.item())

@@ -12,6 +12,7 @@ No CPU fallback: constructing a model without a visible B200 raises ``MfgpError`
 """
 import ctypes
 import re
+import threading
 
 import numpy as np
 import torch
@@ -87,6 +88,7 @@ class _Likelihood:
     def variance(self, v):   # GPy: assignment triggers parameters_changed -> re-inference
         self._m._noise = float(np.asarray(v).ravel()[0])
         self._m._dirty = True
+        self._m._version += 1
 
 
 class _ParamView:
@@ -120,15 +122,22 @@ _ws_pool = {}
 
 
 def workspace(device, nbytes):
-    """Grow-only scratch tensor per device (caller-owned scratch of the C-ABI calls)."""
-    key = int(device)
+    """Grow-only scratch tensor per (device, Python thread) -- the same ownership as the C-ABI handle
+    (_ffi.get_handle): calls of one thread are stream-ordered, so they can share one scratch; two
+    threads never alias it."""
+    key = (int(device), threading.get_ident())
     n = (int(nbytes) + 7) // 8
     cur = _ws_pool.get(key)
     if cur is None or cur.numel() < n:
         _ws_pool[key] = None
-        cur = torch.empty(n, dtype=torch.float64, device="cuda:%d" % key)
+        cur = torch.empty(n, dtype=torch.float64, device="cuda:%d" % key[0])
         _ws_pool[key] = cur
     return cur
+
+
+def release_workspaces():
+    """Drop every cached scratch tensor (bench.py between sections)."""
+    _ws_pool.clear()
 
 
 def to_device(arr, device):
@@ -172,6 +181,7 @@ class GPRegression:
         self._theta_c = (ctypes.c_double * 8)()
         self.last_jitter = 0.0
         self._a_holds_L = False
+        self._version = 0                                   # bumped whenever data or hyper-parameters change
 
     # -- parameters ------------------------------------------------------------------------
     @property
@@ -186,6 +196,7 @@ class GPRegression:
         self.kern.param_array[:] = theta[:-1]
         self._noise = float(theta[-1])
         self._dirty = True
+        self._version += 1
 
     def _match(self, pattern):
         rx = re.compile(pattern)
@@ -275,38 +286,46 @@ class GPRegression:
     def append_point(self, x_row, y):
         """Append one training point at FIXED hyper-parameters with the O(N^2) bordered update
         (mfgp_append_point) instead of refactorising: what one adaptation step adds
-        (src/abstractMFGP.py:320,354) when the hyper-parameters are not re-optimised."""
+        (src/abstractMFGP.py:320,354) when the hyper-parameters are not re-optimised.
+        The grown inputs and buffers are built in locals and committed together with N += 1 only after
+        the call has been validated; on a failure the model keeps its N-point state."""
         self._ensure_posterior()
         h = _ffi.get_handle(self.device)
         x_row = np.asarray(x_row, dtype=np.float64).reshape(1, self.D)
-        self.X = np.vstack([self.X, x_row])
-        self.Y = np.vstack([self.Y, np.asarray(y, dtype=np.float64).reshape(1, 1)])
-        self._dX = to_device(self.X, self.device)
-        self._dy = to_device(self.Y.ravel(), self.device)
+        X = np.vstack([self.X, x_row])
+        Y = np.vstack([self.Y, np.asarray(y, dtype=np.float64).reshape(1, 1)])
+        dX = to_device(X, self.device)
+        dy = to_device(Y.ravel(), self.device)
+        dA, dW, dalpha, npad = self._dA, self._dW, self._dalpha, self.npad
         if self.N % TILE == 0:                       # padded buffers are full: add one 128-tile
-            old, new = self.npad, self.npad + TILE
+            old, npad = self.npad, self.npad + TILE
             dev = self._dA.device
-            for name in ("_dA", "_dW"):
-                buf = torch.zeros((new, new), dtype=torch.float64, device=dev)
-                buf[:old, :old] = getattr(self, name)
-                idx = torch.arange(old, new, device=dev)
+            grown = []
+            for src in (self._dA, self._dW):
+                buf = torch.zeros((npad, npad), dtype=torch.float64, device=dev)
+                buf[:old, :old] = src
+                idx = torch.arange(old, npad, device=dev)
                 buf[idx, idx] = 1.0                  # identity pad block
-                setattr(self, name, buf)
-            alpha = torch.zeros(new, dtype=torch.float64, device=dev)
-            alpha[:old] = self._dalpha
-            self._dalpha = alpha
-            self.npad = new
+                grown.append(buf)
+            dA, dW = grown
+            dalpha = torch.zeros(npad, dtype=torch.float64, device=dev)
+            dalpha[:old] = self._dalpha
         theta = self.param_array
         out = (ctypes.c_double * 4)()
         rc = h.lib.mfgp_append_point(
-            h.h, self.kern.kind, self._dX.data_ptr(), self._dy.data_ptr(), self.N, self.D, self.kern.d,
-            self._theta_ptr(theta), len(theta), float(self.last_jitter), self._dA.data_ptr(),
-            self._dW.data_ptr(), self._dalpha.data_ptr(), int(self._a_holds_L),
-            ctypes.cast(out, ctypes.c_void_p))
+            h.h, self.kern.kind, dX.data_ptr(), dy.data_ptr(), self.N, self.D, self.kern.d,
+            self._theta_ptr(theta), len(theta), float(self.last_jitter), dA.data_ptr(),
+            dW.data_ptr(), dalpha.data_ptr(), int(self._a_holds_L), ctypes.cast(out, ctypes.c_void_p))
+        if rc < 0:
+            # bad argument / CUDA failure: the (possibly half-written) new row sits outside the N-point state
+            # when the buffers were grown, inside its pad otherwise -- refactorise lazily either way
+            self._dirty = True
+            h.check(rc)
+        self.X, self.Y, self._dX, self._dy = X, Y, dX, dy
+        self._dA, self._dW, self._dalpha, self.npad = dA, dW, dalpha, npad
         self.N += 1
-        if rc != 0:                                  # new pivot not positive (or failure): refactorise
-            if rc < 0:
-                h.check(rc)
+        self._version += 1
+        if rc > 0:                                   # new pivot not positive: refactorise (jitter schedule)
             self._dirty = True
             self._ensure_posterior()
             return self

@@ -50,12 +50,17 @@ def gauss_legendre_tensor_grid(n_per_dim, lower, upper):
 
 class LegendrePCE(AbstractGPC):
 
-    def __init__(self, function, lower_bound, upper_bound, polynomial_order=8, quadrature_order=8, device=0):
+    def __init__(self, function, lower_bound, upper_bound, polynomial_order=8, quadrature_order=8, device=None):
         self.lower_bound = np.asarray(lower_bound, dtype=np.float64).ravel()
         self.upper_bound = np.asarray(upper_bound, dtype=np.float64).ravel()
         assert self.lower_bound.shape == self.upper_bound.shape and np.all(self.upper_bound > self.lower_bound)
         self.dim = self.lower_bound.shape[0]
-        self.device = device
+        # the device of the wrapped model (one process per GPU: rank r's model lives on cuda:LOCAL_RANK),
+        # else torch's current device; nodes and weights must sit where the model's handle runs
+        owner = getattr(function, "__self__", function)
+        if device is None:
+            device = getattr(owner, "device", None)
+        self.device = gp.current_device() if device is None else int(device)
         self.coefficients = None
         self._set_order(polynomial_order, quadrature_order)
         super().__init__(function)
@@ -74,6 +79,9 @@ class LegendrePCE(AbstractGPC):
     def _evaluate_on_device(self):
         fn = self.function
         owner = getattr(fn, "__self__", None)
+        owner_dev = getattr(owner if owner is not None else fn, "device", None)
+        assert owner_dev is None or int(owner_dev) == self.device, \
+            "quadrature nodes live on cuda:%d but the model on cuda:%s" % (self.device, owner_dev)
         if hasattr(fn, "device_predict"):
             return fn.device_predict(self._d_nodes)
         for obj in (fn, owner):
