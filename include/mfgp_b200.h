@@ -110,6 +110,18 @@ int mfgp_lml_grad_timed(mfgp_handle_t h, int kind, const double* d_X, const doub
                         int D, int d, const double* h_theta, int P, double jitter, double* d_A,
                         double* d_W, double* d_alpha, double* h_lml, double* h_grad, double* h_ms);
 
+/* Batched objective at the reference's own problem sizes (N <= 128: 5-30 high-fidelity points refitted by
+ * 1 + 6 L-BFGS-B runs per adaptation step, src/abstractMFGP.py:131-137, src/gpc/mfgp_gpc.py:17-20).
+ * B hyper-parameter vectors (h_thetas: HOST (B, P)) are evaluated by ONE launch, one CTA each, on the same
+ * training data; only scalars come back -- no factor is written.  This is what lets the independent restarts
+ * of optimize_restarts (src/abstractMFGP.py:137) run in lock-step on one GPU.
+ * h_lml (B); h_grad (B, P) or NULL (no gradient); h_info (B): 0, or the 1-based first non-positive pivot of
+ * that vector's factorisation (the caller replays GPy's jitter schedule for it).  Returns 0 or <0. */
+int mfgp_lml_grad_batch_max(void);   /* vectors per launch (larger B is processed in slices) */
+int mfgp_lml_grad_batch(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N, int D, int d,
+                        const double* h_thetas, int P, int B, double jitter, double* h_lml, double* h_grad,
+                        int* h_info);
+
 /* Bordered update at FIXED theta: one training point appended, as the
  * adaptation loop does once per step (src/abstractMFGP.py:320,354), in O(N^2) instead of refactorising:
  *   l = W k, L[N] = [l, l_nn], l_nn = sqrt(K(a,a) + noise + 1e-8 + jitter - |l|^2),
@@ -155,6 +167,34 @@ int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t*
                     unsigned long long seed, long long m0, int include_lf_noise,
                     int include_hf_noise, const double* d_weights, double* d_mean, double* d_var,
                     double* h_wsum, double* d_ws, size_t ws_bytes);
+
+/* K7 through a chain of L >= 2 fidelity levels (recursive NARGP, README.md:13 / Perdikaris et al. 2017 eq. 2.9-2.10;
+ * SURVEY.md section 8f rank 4): levels[0] is a GP on x (D = d), every levels[t >= 1] a GP on [x, z] (D = d + 1).
+ *   z_1 = mu_0(x) + sd_0(x) eps_1;   (mu_t, v_t) = level t at [x, z_t];   z_{t+1} = mu_t + sqrt(v_t) eps_{t+1}
+ * per sample, and mean = mean_s mu_{L-1,s}, var = mean_s v_{L-1,s} + var_s mu_{L-1,s}.  L = 2 is mfgp_predict_mc.
+ * d_eps: (L-1, M, S) standard normals or NULL -> Philox4x32-10, key seed + (j-1) * 0x9E3779B97F4A7C15 for the j-th
+ * sampling, counter (m0+m)*S+s (so j = 1 draws what mfgp_predict_mc draws).  include_lower_noise: the sampled
+ * variances v_t (t < L-1) include that level's noise variance; include_top_noise: the returned one does. */
+int mfgp_predict_mc_chain(mfgp_handle_t h, const mfgp_level_t* const* levels, int L, const double* d_Xtest,
+                          long long M, int S, const double* d_eps, unsigned long long seed, long long m0,
+                          int include_lower_noise, int include_top_noise, const double* d_weights,
+                          double* d_mean, double* d_var, double* h_wsum, double* d_ws, size_t ws_bytes);
+
+/* K7 with the low-fidelity posterior sampled JOINTLY across the test points (SURVEY.md section 8f rank 4,
+ * "full-covariance LF sampling for small M"; E = 1 models, M <= 16384):
+ *   Sigma_l = K_l(X*, X*) - (W_l K_l*)^T (W_l K_l*) + ((include_lf_noise ? noise_l : 0) + lf_jitter) I   (M x M),
+ *   z_s = mu_l + chol(Sigma_l) eps_s,   eps: d_eps (M, S) or NULL -> Philox counter m*S+s,
+ * so that every sample s is one coherent low-fidelity function; mean / var aggregate as in mfgp_predict_mc
+ * (their expectation is the same -- they only depend on the marginals), and d_path_wsum (S, DEVICE, may be
+ * NULL) receives the per-path functional sum_m w_m mu_s(x_m): the distribution of the PCE mean over
+ * low-fidelity function draws.  Returns >0 (1-based pivot) if Sigma_l is not positive definite: raise lf_jitter.
+ * Not sharded: all M points belong to one covariance.  Scratch: mfgp_predict_mc_joint_ws_bytes. */
+size_t mfgp_predict_mc_joint_ws_bytes(int N_l, int N_h, long long M, int S);
+int mfgp_predict_mc_joint(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
+                          const double* d_Xtest, long long M, int S, const double* d_eps,
+                          unsigned long long seed, int include_lf_noise, int include_hf_noise,
+                          double lf_jitter, const double* d_weights, double* d_mean, double* d_var,
+                          double* d_path_wsum, double* d_ws, size_t ws_bytes);
 
 /* K7 for models with delays (GPDF / GPDFC: E = n*d + 1 augmented columns, 1 <= E <= 8).  The
  * low-fidelity posterior at the E locations x + o_e tau of a test point is JOINT: mu_l in R^E,

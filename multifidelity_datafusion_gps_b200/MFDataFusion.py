@@ -232,7 +232,7 @@ class MultifidelityDataFusion(AbstractMFGP):
         npl, nph, d = self.lf_model.npad, self.hf_model.npad, self.input_dim
         if E == 1:
             if ws_bytes is None:
-                per_col = (nph + d + 3) * 8
+                per_col = (nph + d + 4) * 8               # Ks row + [x, z] + mean, sum of squares, sample
                 want = 16 * M + 148 * 128 * 4 * per_col
                 need = 16 * M + max((S + 256) * per_col, (npl + 1) * 128 * 8) + 4096
                 ws_bytes = max(min(want, 12 << 30), need)     # ~4 column tiles per SM up to N_h = 16384
@@ -268,14 +268,53 @@ class MultifidelityDataFusion(AbstractMFGP):
         h.check(rc)
         return mean, var, (wsum.value if wsum is not None else None)
 
+    def predict_mc_joint_device(self, dX, n_samples=100, d_eps=None, seed=0, d_weights=None,
+                                include_lf_noise=True, lf_jitter=0.0):
+        """Monte-Carlo propagation with the low-fidelity posterior sampled JOINTLY across the test points
+        (full M x M predictive covariance; E = 1 models, small M): every sample is one coherent low-fidelity
+        function draw.  dX (M, d) CUDA -> (mean (M,), var (M,), per-path weighted sums (S,)): path s gives
+        sum_m w_m mu_s(x_m), e.g. the PCE mean under that draw (weights None -> plain sums).  d_eps: (M, S)."""
+        assert self.data_driven_lf_approach, "MC propagation needs a data-driven low-fidelity GP"
+        assert self.augm_iterator.new_entries_count() == 1, "joint sampling across test points serves E = 1 models"
+        h = _ffi.get_handle(self.device)
+        self._apply_add_noise()
+        lf, hf = self.lf_model.level_struct(), self.hf_model.level_struct()
+        M, S = int(dX.shape[0]), int(n_samples)
+        mean = torch.empty(M, dtype=torch.float64, device=dX.device)
+        var = torch.empty(M, dtype=torch.float64, device=dX.device)
+        paths = torch.empty(S, dtype=torch.float64, device=dX.device)
+        ws = gp.workspace(self.device, h.lib.mfgp_predict_mc_joint_ws_bytes(self.lf_model.N, self.hf_model.N, M, S))
+        rc = h.lib.mfgp_predict_mc_joint(
+            h.h, ctypes.byref(lf), ctypes.byref(hf), dX.data_ptr(), M, S,
+            d_eps.data_ptr() if d_eps is not None else None, int(seed), int(include_lf_noise), 1,
+            float(lf_jitter), d_weights.data_ptr() if d_weights is not None else None, mean.data_ptr(),
+            var.data_ptr(), paths.data_ptr(), ws.data_ptr(), ws.numel() * 8)
+        if rc > 0:
+            raise np.linalg.LinAlgError(
+                "joint low-fidelity covariance of the test points is not positive definite (pivot %d); "
+                "pass lf_jitter" % rc)
+        h.check(rc)
+        return mean, var, paths
+
     def predict_mc(self, X_test, n_samples=100, eps=None, seed=0, weights=None, include_lf_noise=True,
-                   m0=0, lf_jitter=0.0):
+                   m0=0, lf_jitter=0.0, joint=False):
         """NumPy front end of predict_mc_device.  eps: optional standard normals, (M, S[, 1]) for E = 1,
         (M, S, E) for models with delays.  m0: global index of the first test point (keys the in-kernel
         generator when eps is None).  lf_jitter: added to the diagonal of the joint LF covariance (E > 1).
         Returns (mean (M,1), var (M,1)); with `weights` also sets ``self.last_pce_mean``."""
         assert X_test.ndim == 2 and X_test.shape[1] == self.input_dim
         E = self.augm_iterator.new_entries_count()
+        if joint:
+            # joint=True: the LF posterior is sampled jointly ACROSS the test points (predict_mc_joint_device);
+            # sets ``self.last_pce_paths`` (S,): the weighted sum of every sample path
+            d_eps = None if eps is None else gp.to_device(
+                np.asarray(eps, dtype=np.float64).reshape(X_test.shape[0], n_samples), self.device)
+            d_w = gp.to_device(np.asarray(weights).ravel(), self.device) if weights is not None else None
+            mean, var, paths = self.predict_mc_joint_device(gp.to_device(X_test, self.device), n_samples, d_eps,
+                                                            seed, d_w, include_lf_noise, lf_jitter)
+            self.last_pce_paths = paths.cpu().numpy()
+            self.last_pce_mean = float(self.last_pce_paths.mean()) if weights is not None else None
+            return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]
         d_eps = None
         if eps is not None:
             eps = np.asarray(eps, dtype=np.float64).reshape(X_test.shape[0], n_samples, E)

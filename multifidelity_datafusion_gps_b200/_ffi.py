@@ -21,8 +21,9 @@ TILE = 128
 EXPORTS = [
     "mfgp_version", "mfgp_padded_n", "mfgp_create", "mfgp_destroy", "mfgp_set_stream",
     "mfgp_last_error", "mfgp_launch_count", "mfgp_profile_enable", "mfgp_profile_read", "mfgp_assemble", "mfgp_factorize", "mfgp_lml_grad",
-    "mfgp_lml_grad_timed", "mfgp_append_point", "mfgp_potrf", "mfgp_trtri", "mfgp_lauum", "mfgp_predict_ws_bytes",
-    "mfgp_predict", "mfgp_augment", "mfgp_predict_mc", "mfgp_predict_mc_delays", "mfgp_fill_normal",
+    "mfgp_lml_grad_timed", "mfgp_lml_grad_batch_max", "mfgp_lml_grad_batch", "mfgp_append_point", "mfgp_potrf", "mfgp_trtri", "mfgp_lauum", "mfgp_predict_ws_bytes",
+    "mfgp_predict", "mfgp_augment", "mfgp_predict_mc", "mfgp_predict_mc_chain", "mfgp_predict_mc_joint_ws_bytes", "mfgp_predict_mc_joint",
+    "mfgp_predict_mc_delays", "mfgp_fill_normal",
     "mfgp_argmax", "mfgp_pce_ws_bytes", "mfgp_pce_project",
 ]
 
@@ -78,6 +79,7 @@ def load_library():
     lib.mfgp_append_point.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, c_dbl, vp, vp, vp, c_int, vp]
     lib.mfgp_lml_grad.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, c_dbl, vp, vp, vp, vp, vp]
     lib.mfgp_lml_grad_timed.argtypes = lib.mfgp_lml_grad.argtypes + [vp]
+    lib.mfgp_lml_grad_batch.argtypes = [vp, c_int, vp, vp, c_int, c_int, c_int, vp, c_int, c_int, c_dbl, vp, vp, vp]
     lib.mfgp_potrf.argtypes = [vp, vp, vp, c_int]
     lib.mfgp_trtri.argtypes = [vp, vp, vp, c_int]
     lib.mfgp_lauum.argtypes = [vp, vp, vp, c_int]
@@ -87,6 +89,12 @@ def load_library():
     lib.mfgp_augment.argtypes = [vp, ctypes.POINTER(Level), vp, c_ll, vp, c_int, c_dbl, vp, vp, c_sz]
     lib.mfgp_predict_mc.argtypes = [vp, ctypes.POINTER(Level), ctypes.POINTER(Level), vp, c_ll, c_int,
                                     vp, c_ull, c_ll, c_int, c_int, vp, vp, vp, vp, vp, c_sz]
+    lib.mfgp_predict_mc_chain.argtypes = [vp, vp, c_int, vp, c_ll, c_int, vp, c_ull, c_ll, c_int, c_int, vp, vp,
+                                          vp, vp, vp, c_sz]
+    lib.mfgp_predict_mc_joint_ws_bytes.argtypes = [c_int, c_int, c_ll, c_int]
+    lib.mfgp_predict_mc_joint_ws_bytes.restype = c_sz
+    lib.mfgp_predict_mc_joint.argtypes = [vp, ctypes.POINTER(Level), ctypes.POINTER(Level), vp, c_ll, c_int, vp,
+                                          c_ull, c_int, c_int, c_dbl, vp, vp, vp, vp, vp, c_sz]
     lib.mfgp_predict_mc_delays.argtypes = [vp, ctypes.POINTER(Level), ctypes.POINTER(Level), vp, c_ll, vp, c_int,
                                            c_dbl, c_int, vp, c_ull, c_ll, c_int, c_int, c_dbl, vp, vp, vp, vp,
                                            vp, c_sz]
@@ -97,7 +105,8 @@ def load_library():
     lib.mfgp_pce_project.argtypes = [vp, vp, vp, vp, c_int, vp, vp, c_ll, vp, c_int, c_int, vp, vp, vp, c_sz]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("mfgp_last_error", "mfgp_launch_count", "mfgp_predict_ws_bytes", "mfgp_pce_ws_bytes"):
+        if name not in ("mfgp_last_error", "mfgp_launch_count", "mfgp_predict_ws_bytes", "mfgp_pce_ws_bytes",
+                        "mfgp_predict_mc_joint_ws_bytes"):
             fn.restype = c_int
     _lib = lib
     return lib

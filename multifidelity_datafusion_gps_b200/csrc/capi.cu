@@ -24,7 +24,15 @@ int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, 
                         const double* alpha, const double* Xtest, const double* mu_l,
                         const double* sd_l, const double* eps, unsigned long long seed,
                         long long m_global0, long long m_lo, long long npts, int S,
-                        long long cols_pad, double* Ks, double* mu_c);
+                        long long cols_pad, double* Ks, double* mu_c, const double* zcol, long long z_off,
+                        long long ldz);
+int sample_cols_launch(mfgp_ctx* h, const double* mu_c, const double* v_c, const double* eps,
+                       unsigned long long key, long long m_global0, long long m_lo, long long ncols, int S,
+                       double* z);
+int fill_normal_padded_launch(mfgp_ctx* h, const double* eps, unsigned long long seed, long long M, int S,
+                              long long rows, long long ldE, double* E);
+int path_wsum_launch(mfgp_ctx* h, const double* mu_c, const double* w, long long m_lo, long long npts, int S,
+                     double* path);
 int append_point_launch(mfgp_ctx* h, const double* k, int N, int npad, double kaa, double* A, double* W,
                         int write_L, double* l_tmp, double* t_tmp, double* d_out2);
 int mc_max_samples();
@@ -63,6 +71,21 @@ struct DeviceGuard {
   if (!(h)) return -1;  \
   DeviceGuard _device_guard((h)->device)
 
+// -1 / (2 len^2), kept finite.  The optimiser's line search visits lengthscales down to the denormals
+// (L-BFGS-B's first long steps on the reference's 1-D curve evaluate len = 5.6e-309): GPy then gets r = dist/len
+// -> huge, exp(-r^2/2) -> 0 off the diagonal and K = variance * I, a perfectly valid (if useless) model whose
+// finite LML steers the search back.  With an infinite coefficient the diagonal would be 0 * inf = NaN here and
+// the evaluation would be reported as infeasible, which sends the optimiser somewhere else.  A coefficient of
+// -1e300 gives exactly GPy's matrix: 0 on coincident points, underflow (< 4.5e-308) everywhere else.
+static double inv_len2(double len) {
+  const double a = -0.5 / (len * len);
+  return a < -1e300 ? -1e300 : a;
+}
+
+// d/d len = S / len^3; below 1e-100 every off-diagonal covariance (and with it every term of S) has
+// underflowed, and GPy's gradient is exactly 0 there (-r K G with K = 0) while S / len^3 would be 0 / 0
+static double len_grad(double S, double len) { return len < 1e-100 ? 0.0 : S / (len * len * len); }
+
 int make_kparams(mfgp_ctx* h, int kind, int D, int d, const double* theta, int P, KParams* kp) {
   ARG_CHECK(h, theta != nullptr);
   ARG_CHECK(h, D >= 1 && D <= MFGP_MAX_D && d >= 1 && d <= D);
@@ -74,16 +97,16 @@ int make_kparams(mfgp_ctx* h, int kind, int D, int d, const double* theta, int P
     ARG_CHECK(h, P == 7 && d < D);
     for (int i = 0; i < 6; i++) ARG_CHECK(h, theta[i] > 0.0);
     kp->c12 = theta[0] * theta[2];
-    kp->az = -0.5 / (theta[1] * theta[1]);
-    kp->ax = -0.5 / (theta[3] * theta[3]);
+    kp->az = inv_len2(theta[1]);
+    kp->ax = inv_len2(theta[3]);
     kp->s3 = theta[4];
-    kp->a3 = -0.5 / (theta[5] * theta[5]);
+    kp->a3 = inv_len2(theta[5]);
     kp->kdiag = theta[0] * theta[2] + theta[4];
   } else if (kind == MFGP_KIND_RBF) {
     ARG_CHECK(h, P == 3);
     ARG_CHECK(h, theta[0] > 0.0 && theta[1] > 0.0);
     kp->c12 = theta[0];
-    kp->az = kp->ax = -0.5 / (theta[1] * theta[1]);
+    kp->az = kp->ax = inv_len2(theta[1]);
     kp->s3 = 0.0;
     kp->a3 = 0.0;
     kp->kdiag = theta[0];
@@ -171,7 +194,11 @@ int mfgp_create(int device, mfgp_handle_t* out) {
             cudaMalloc(&h->d_info, 4 * sizeof(int)) == cudaSuccess &&
             cudaMalloc(&h->d_exp_tbl, 256 * sizeof(double)) == cudaSuccess &&
             cudaMallocHost(&h->h_pinned, 64 * sizeof(double)) == cudaSuccess &&
-            cudaMallocHost(&h->h_info, 4 * sizeof(int)) == cudaSuccess;
+            cudaMallocHost(&h->h_info, 4 * sizeof(int)) == cudaSuccess &&
+            cudaHostAlloc(&h->h_batch, 16 * 16 * sizeof(double), cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostAlloc(&h->h_batch_info, 16 * sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer((void**)&h->d_batch, h->h_batch, 0) == cudaSuccess &&
+            cudaHostGetDevicePointer((void**)&h->d_batch_info, h->h_batch_info, 0) == cudaSuccess;
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
   for (int i = 0; ok && i < 3 * 64 + 2; i++)
     ok = cudaEventCreateWithFlags(&h->ev_la[i], cudaEventDisableTiming) == cudaSuccess;
@@ -186,7 +213,7 @@ int mfgp_create(int device, mfgp_handle_t* out) {
     for (int j = 0; j < 256; j++) tbl[j] = (double)exp2l((long double)j / 256.0L);
     ok = cudaMemcpy(h->d_exp_tbl, tbl, sizeof(tbl), cudaMemcpyHostToDevice) == cudaSuccess;
   }
-  if (!ok || small_gp_configure(h) != 0 || linalg_configure(h) != 0 || assemble_configure(h) != 0 || predict_configure(h) != 0) {
+  if (!ok || small_gp_configure(h) != 0 || small_batch_configure(h) != 0 || linalg_configure(h) != 0 || assemble_configure(h) != 0 || predict_configure(h) != 0) {
     snprintf(g_err, sizeof(g_err), "mfgp_create: scratch allocation / kernel configuration failed: %s",
              cudaGetErrorString(cudaGetLastError()));
     delete h;
@@ -204,6 +231,8 @@ int mfgp_destroy(mfgp_handle_t h) {
   cudaFree(h->d_exp_tbl);
   cudaFreeHost(h->h_pinned);
   cudaFreeHost(h->h_info);
+  cudaFreeHost(h->h_batch);
+  cudaFreeHost(h->h_batch_info);
   for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 3 * 64 + 2; i++) cudaEventDestroy(h->ev_la[i]);
   if (h->s_hi) cudaStreamDestroy(h->s_hi);
@@ -318,15 +347,15 @@ static void grads_from_sums(const KParams& kp, const double* S, double* g) {
   const double* th = kp.theta;
   if (kp.kind == MFGP_KIND_COMPOSITE) {
     g[0] = S[0] / th[0];
-    g[1] = S[1] / (th[1] * th[1] * th[1]);
+    g[1] = len_grad(S[1], th[1]);
     g[2] = S[0] / th[2];
-    g[3] = S[2] / (th[3] * th[3] * th[3]);
+    g[3] = len_grad(S[2], th[3]);
     g[4] = S[3] / th[4];
-    g[5] = S[4] / (th[5] * th[5] * th[5]);
+    g[5] = len_grad(S[4], th[5]);
     g[6] = S[5];
   } else {
     g[0] = S[0] / th[0];
-    g[1] = (S[1] + S[2]) / (th[1] * th[1] * th[1]);
+    g[1] = len_grad(S[1] + S[2], th[1]);
     g[2] = S[5];
   }
 }
@@ -375,6 +404,37 @@ int mfgp_lml_grad(mfgp_handle_t h, int kind, const double* d_X, const double* d_
                   double* d_alpha, double* h_lml, double* h_grad) {
   return mfgp_lml_grad_timed(h, kind, d_X, d_y, N, D, d, h_theta, P, jitter, d_A, d_W, d_alpha,
                              h_lml, h_grad, nullptr);
+}
+
+int mfgp_lml_grad_batch_max(void) { return small_batch_max(); }
+
+int mfgp_lml_grad_batch(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N, int D, int d,
+                        const double* h_thetas, int P, int B, double jitter, double* h_lml, double* h_grad,
+                        int* h_info) {
+  ENTER(h);
+  ARG_CHECK(h, d_X && d_y && h_thetas && h_lml && h_info && B >= 1 && N >= 1 && N <= MFGP_TILE);
+  const int bmax = small_batch_max();
+  KParams kps[16];
+  double diag_add[16];
+  for (int b0 = 0; b0 < B; b0 += bmax) {
+    const int nb = B - b0 < bmax ? B - b0 : bmax;
+    int rc;
+    for (int b = 0; b < nb; b++) {
+      if ((rc = make_kparams(h, kind, D, d, h_thetas + (long)(b0 + b) * P, P, &kps[b]))) return rc;
+      diag_add[b] = kps[b].noise + JITTER_CONST + jitter;
+    }
+    // the kernel writes its scalars straight into mapped pinned host memory: one launch + one sync
+    if ((rc = small_lml_batch_launch(h, kps, diag_add, nb, d_X, d_y, N, h->d_batch, h->d_batch_info,
+                                     h_grad != nullptr)))
+      return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < nb; b++) {
+      h_lml[b0 + b] = h->h_batch[b * 16];
+      h_info[b0 + b] = h->h_batch_info[b];
+      if (h_grad) grads_from_sums(kps[b], h->h_batch + b * 16 + 8, h_grad + (long)(b0 + b) * P);
+    }
+  }
+  return 0;
 }
 
 int mfgp_append_point(mfgp_handle_t h, int kind, const double* d_X, const double* d_y, int N, int D,
@@ -510,22 +570,35 @@ int mfgp_augment(mfgp_handle_t h, const mfgp_level_t* lf, const double* d_X, lon
   return 0;
 }
 
-int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
-                    const double* d_Xtest, long long M, int S, const double* d_eps,
-                    unsigned long long seed, long long m0, int include_lf_noise,
-                    int include_hf_noise, const double* d_weights, double* d_mean, double* d_var,
-                    double* h_wsum, double* d_ws, size_t ws_bytes) {
-  ENTER(h);
-  KParams kl, kh;
+// K7 through a chain of L >= 2 levels; L = 2 is mfgp_predict_mc.  levels[0]: GP on x (D = d); levels[t >= 1]:
+// GP on [x, z] (D = d + 1).  Sampling #j (the value level j-1 hands to level j) draws from Philox key
+// seed + (j-1) * golden-ratio increment with counter (m0 + m) S + s, or from d_eps[(j-1) M S + m S + s].
+#define MFGP_MAX_LEVELS 8
+static int mc_chain_impl(mfgp_ctx* h, const mfgp_level_t* const* levels, int L, const double* d_Xtest,
+                         long long M, int S, const double* d_eps, unsigned long long seed, long long m0,
+                         int include_lower_noise, int include_top_noise, const double* d_weights,
+                         double* d_mean, double* d_var, double* h_wsum, double* d_ws, size_t ws_bytes) {
+  ARG_CHECK(h, levels && L >= 2 && L <= MFGP_MAX_LEVELS);
+  KParams kp[MFGP_MAX_LEVELS];
   int rc;
-  if ((rc = level_kparams(h, lf, &kl))) return rc;
-  if ((rc = level_kparams(h, hf, &kh))) return rc;
+  for (int t = 0; t < L; t++) {
+    ARG_CHECK(h, levels[t] != nullptr);
+    if ((rc = level_kparams(h, levels[t], &kp[t]))) return rc;
+    ARG_CHECK(h, levels[t]->d_W != nullptr);
+  }
+  const mfgp_level_t* lf = levels[0];
   const int d = lf->D;
-  // E = 1: NARGP (composite kernel on [x, z]) or GPDF without delays (one RBF over [x, z]: az == ax, so
-  // the same code runs with the split at d)
-  ARG_CHECK(h, hf->D == d + 1 && (hf->d == d || hf->kind == MFGP_KIND_RBF));
-  kh.d = d;
-  ARG_CHECK(h, lf->d_W && hf->d_W && d_Xtest && d_mean && d_var && d_ws && S >= 1 && M >= 0);
+  int npad_max = 0;
+  for (int t = 1; t < L; t++) {
+    // E = 1: NARGP (composite kernel on [x, z]) or GPDF without delays (one RBF over [x, z]: az == ax, so
+    // the same code runs with the split at d)
+    ARG_CHECK(h, levels[t]->D == d + 1 && (levels[t]->d == d || levels[t]->kind == MFGP_KIND_RBF));
+    kp[t].d = d;
+    const int np_t = mfgp_padded_n(levels[t]->N);
+    if (np_t > npad_max) npad_max = np_t;
+  }
+  ARG_CHECK(h, d_Xtest && d_mean && d_var && d_ws && S >= 1 && M >= 0);
+  ARG_CHECK(h, L == 2 || S <= mc_max_samples());
   if (M == 0) return 0;
   const long long wsd = (long long)(ws_bytes / sizeof(double));
   ARG_CHECK(h, wsd > 2 * M);
@@ -537,49 +610,166 @@ int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t*
   // the trmm_sumsq / cross_gen classes hold the high-fidelity launches only)
   const int prof_saved = h->prof_on;
   h->prof_on = 0;
-  rc = predict_impl(h, lf, kl, d_Xtest, M, mu_l, sd_l, include_lf_noise, rest,
+  rc = predict_impl(h, lf, kp[0], d_Xtest, M, mu_l, sd_l, include_lower_noise, rest,
                     (size_t)restd * sizeof(double));
   h->prof_on = prof_saved;
   if (rc) return rc;
   if ((rc = sqrt_launch(h, sd_l, M))) return rc;
-  // high-fidelity level over (point, sample) columns
-  const int npad = mfgp_padded_n(hf->N);
+  // upper levels over (point, sample) columns
   const int D = d + 1;
-  const long long per_col = (long long)npad + D + 2;
+  const long long per_col = (long long)npad_max + D + 3;
   long long max_cols = restd / per_col / 128 * 128;
   ARG_CHECK(h, max_cols >= 128);
   long long pm = max_cols / S;
   ARG_CHECK(h, pm >= 1);   // the scratch must hold all S samples of at least one point
   if (pm > M) pm = M;
   const long long cp_max = (pm * S + 127) / 128 * 128;
-  double* Xq = rest;
+  double* Xq = rest;                 // (cp_max, D): rows [x, z] when S exceeds the generator's sample limit
   double* mu_c = Xq + cp_max * D;
   double* ss = mu_c + cp_max;
-  double* Ks = ss + cp_max;
+  double* zcol = ss + cp_max;
+  double* Ks = zcol + cp_max;
   for (long long m_lo = 0; m_lo < M; m_lo += pm) {
     const long long npts = (M - m_lo < pm) ? (M - m_lo) : pm;
     const long long ncols = npts * S;
     const long long cols_pad = (ncols + 127) / 128 * 128;
-    if (S <= mc_max_samples()) {
-      // one CTA per test point: x-dependent kernel factors shared by its S samples (1 exp / element)
-      if ((rc = cross_gen_mc_launch(h, kh, hf->d_X, hf->N, npad, hf->d_alpha, d_Xtest, mu_l, sd_l, d_eps,
-                                    seed, m0, m_lo, npts, S, cols_pad, Ks, mu_c)))
-        return rc;
-    } else {
-      if ((rc = build_mc_rows_launch(h, d_Xtest, mu_l, sd_l, d_eps, seed, m0, m_lo, ncols, S, d, Xq)))
-        return rc;
-      if ((rc = cross_gen_launch(h, kh, hf->d_X, hf->N, npad, hf->d_alpha, Xq, ncols, cols_pad, Ks, mu_c)))
-        return rc;
+    for (int t = 1; t < L; t++) {
+      const mfgp_level_t* lv = levels[t];
+      const int npad = mfgp_padded_n(lv->N);
+      const unsigned long long key = seed + (unsigned long long)(t - 1) * 0x9E3779B97F4A7C15ULL;
+      const double* eps_t = d_eps ? d_eps + (long long)(t - 1) * M * S : nullptr;
+      if (t == 1) {
+        if (S <= mc_max_samples()) {
+          // one CTA per test point: x-dependent kernel factors shared by its S samples (1 exp / element)
+          if ((rc = cross_gen_mc_launch(h, kp[1], lv->d_X, lv->N, npad, lv->d_alpha, d_Xtest, mu_l, sd_l, eps_t,
+                                        key, m0, m_lo, npts, S, cols_pad, Ks, mu_c, nullptr, 0, 0)))
+            return rc;
+        } else {
+          if ((rc = build_mc_rows_launch(h, d_Xtest, mu_l, sd_l, eps_t, key, m0, m_lo, ncols, S, d, Xq)))
+            return rc;
+          if ((rc = cross_gen_launch(h, kp[1], lv->d_X, lv->N, npad, lv->d_alpha, Xq, ncols, cols_pad, Ks, mu_c)))
+            return rc;
+        }
+      } else {
+        // z = mu + sqrt(v) eps of the level below, per (point, sample) column, then this level at [x, z]
+        if ((rc = sample_cols_launch(h, mu_c, ss, eps_t, key, m0, m_lo, ncols, S, zcol))) return rc;
+        if ((rc = cross_gen_mc_launch(h, kp[t], lv->d_X, lv->N, npad, lv->d_alpha, d_Xtest, nullptr, nullptr,
+                                      nullptr, 0, m0, m_lo, npts, S, cols_pad, Ks, mu_c, zcol, 0, S)))
+          return rc;
+      }
+      if ((rc = trmm_sumsq(h, lv->d_W, npad, Ks, cols_pad, ss))) return rc;
+      const int with_noise = (t == L - 1) ? include_top_noise : include_lower_noise;
+      if ((rc = finish_var_launch(h, ss, ncols, kp[t].kdiag, with_noise ? kp[t].noise : 0.0, ss))) return rc;
     }
-    if ((rc = trmm_sumsq(h, hf->d_W, npad, Ks, cols_pad, ss))) return rc;
-    if ((rc = finish_var_launch(h, ss, ncols, kh.kdiag, include_hf_noise ? kh.noise : 0.0, ss)))
-      return rc;
     if ((rc = mc_aggregate_launch(h, mu_c, ss, npts, S, d_mean + m_lo, d_var + m_lo))) return rc;
   }
   if (h_wsum) {
     if ((rc = wdot_launch(h, d_weights, d_mean, M, h->d_scalars + 20))) return rc;
     if ((rc = fetch_scalars(h, 24))) return rc;
     h_wsum[0] += h->h_pinned[20];
+  }
+  return 0;
+}
+
+int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
+                    const double* d_Xtest, long long M, int S, const double* d_eps,
+                    unsigned long long seed, long long m0, int include_lf_noise,
+                    int include_hf_noise, const double* d_weights, double* d_mean, double* d_var,
+                    double* h_wsum, double* d_ws, size_t ws_bytes) {
+  ENTER(h);
+  const mfgp_level_t* levels[2] = {lf, hf};
+  return mc_chain_impl(h, levels, 2, d_Xtest, M, S, d_eps, seed, m0, include_lf_noise, include_hf_noise,
+                       d_weights, d_mean, d_var, h_wsum, d_ws, ws_bytes);
+}
+
+int mfgp_predict_mc_chain(mfgp_handle_t h, const mfgp_level_t* const* levels, int L, const double* d_Xtest,
+                          long long M, int S, const double* d_eps, unsigned long long seed, long long m0,
+                          int include_lower_noise, int include_top_noise, const double* d_weights,
+                          double* d_mean, double* d_var, double* h_wsum, double* d_ws, size_t ws_bytes) {
+  ENTER(h);
+  return mc_chain_impl(h, levels, L, d_Xtest, M, S, d_eps, seed, m0, include_lower_noise, include_top_noise,
+                       d_weights, d_mean, d_var, h_wsum, d_ws, ws_bytes);
+}
+
+size_t mfgp_predict_mc_joint_ws_bytes(int N_l, int N_h, long long M, int S) {
+  const long long npl = mfgp_padded_n(N_l), nph = mfgp_padded_n(N_h);
+  const long long Mp = (M + 127) / 128 * 128, Sp = ((long long)S + 127) / 128 * 128;
+  const long long fixed = Mp + 2 * Mp * Mp + 2 * Mp * npl + 2 * Mp * Sp;
+  const long long cols = (Mp * (long long)S < 148LL * 128 * 4 ? Mp * (long long)S : 148LL * 128 * 4) + 256 + S;
+  return (size_t)(fixed + cols * (nph + 3)) * sizeof(double);
+}
+
+// K7 with the low-fidelity posterior sampled JOINTLY across the test points (small M): z_s = mu_l + chol(Sigma_l) eps_s
+// with the full M x M predictive covariance Sigma_l = K(X*, X*) - (W_l K_l*)^T (W_l K_l*) (+ (noise + jitter) I),
+// so that every sample s is one coherent low-fidelity function draw and per-path functionals
+// (d_path_wsum[s] = sum_m w_m mu_s(x_m), the PCE mean of path s) are meaningful.
+int mfgp_predict_mc_joint(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
+                          const double* d_Xtest, long long M, int S, const double* d_eps,
+                          unsigned long long seed, int include_lf_noise, int include_hf_noise,
+                          double lf_jitter, const double* d_weights, double* d_mean, double* d_var,
+                          double* d_path_wsum, double* d_ws, size_t ws_bytes) {
+  ENTER(h);
+  KParams kl, kh;
+  int rc;
+  if ((rc = level_kparams(h, lf, &kl))) return rc;
+  if ((rc = level_kparams(h, hf, &kh))) return rc;
+  const int d = lf->D;
+  ARG_CHECK(h, hf->D == d + 1 && (hf->d == d || hf->kind == MFGP_KIND_RBF));
+  kh.d = d;
+  ARG_CHECK(h, lf->d_W && hf->d_W && d_Xtest && d_mean && d_var && d_ws);
+  ARG_CHECK(h, S >= 1 && S <= mc_max_samples() && M >= 1 && M <= 16384);
+  ARG_CHECK(h, ws_bytes >= mfgp_predict_mc_joint_ws_bytes(lf->N, hf->N, M, S));
+  const int npl = mfgp_padded_n(lf->N), nph = mfgp_padded_n(hf->N);
+  const long long Mp = (M + 127) / 128 * 128, Sp = ((long long)S + 127) / 128 * 128;
+  double* mu_l = d_ws;                      // (Mp)
+  double* Sigma = mu_l + Mp;                // (Mp, Mp) -> chol(Sigma_l), lower
+  double* Wt = Sigma + Mp * Mp;             // (Mp, Mp) leaf inverses (scratch of the factorisation)
+  double* Ksl = Wt + Mp * Mp;               // (Mp, npl)
+  double* T = Ksl + Mp * npl;               // (npl, Mp)
+  double* E = T + Mp * npl;                 // (Mp, Sp) standard normals
+  double* Z = E + Mp * Sp;                  // (Mp, Sp) chol(Sigma_l) E
+  double* rest = Z + Mp * Sp;
+  const long long restd = (long long)(ws_bytes / sizeof(double)) - (rest - d_ws);
+  const int prof_saved = h->prof_on;
+  h->prof_on = 0;
+  // joint low-fidelity posterior
+  if ((rc = cross_gen_launch(h, kl, lf->d_X, lf->N, npl, lf->d_alpha, d_Xtest, M, Mp, Ksl, mu_l))) return rc;
+  if ((rc = trmm_store(h, lf->d_W, npl, Ksl, Mp, T))) return rc;
+  if ((rc = assemble_launch(h, kl, d_Xtest, (int)M, (include_lf_noise ? kl.noise : 0.0) + lf_jitter, Sigma, Mp,
+                            MFGP_UPLO_LOWER, (int)Mp)))
+    return rc;
+  if ((rc = syrk_tn_sub(h, T, Mp, npl, Sigma, (int)Mp))) return rc;       // Sigma(lower) -= T^T T
+  if ((rc = potrf_padded(h, Sigma, Wt, (int)Mp, (int)M))) return rc;
+  if ((rc = fetch_scalars(h, 1))) return rc;
+  if (h->h_info[0] != 0) {
+    h->prof_on = prof_saved;
+    return h->h_info[0];                    // joint covariance not positive definite: raise lf_jitter
+  }
+  if ((rc = fill_normal_padded_launch(h, d_eps, seed, M, S, Mp, Sp, E))) return rc;
+  if ((rc = trmm_right_store(h, Sigma, (int)Mp, E, Sp, Z))) return rc;     // Z = chol(Sigma_l) E
+  h->prof_on = prof_saved;
+  if (d_path_wsum) CUDA_TRY(h, cudaMemsetAsync(d_path_wsum, 0, (size_t)S * sizeof(double), h->stream));
+  // high-fidelity level over (point, sample) columns
+  const long long per_col = (long long)nph + 3;
+  long long max_cols = restd / per_col / 128 * 128;
+  ARG_CHECK(h, max_cols >= 128);
+  long long pm = max_cols / S;
+  ARG_CHECK(h, pm >= 1);
+  if (pm > M) pm = M;
+  const long long cp_max = (pm * S + 127) / 128 * 128;
+  double* mu_c = rest;
+  double* ss = mu_c + cp_max;
+  double* Ks = ss + cp_max;
+  for (long long m_lo = 0; m_lo < M; m_lo += pm) {
+    const long long npts = (M - m_lo < pm) ? (M - m_lo) : pm;
+    const long long ncols = npts * S, cols_pad = (ncols + 127) / 128 * 128;
+    if ((rc = cross_gen_mc_launch(h, kh, hf->d_X, hf->N, nph, hf->d_alpha, d_Xtest, mu_l, nullptr, nullptr, 0, 0,
+                                  m_lo, npts, S, cols_pad, Ks, mu_c, Z, m_lo, Sp)))
+      return rc;
+    if ((rc = trmm_sumsq(h, hf->d_W, nph, Ks, cols_pad, ss))) return rc;
+    if ((rc = finish_var_launch(h, ss, ncols, kh.kdiag, include_hf_noise ? kh.noise : 0.0, ss))) return rc;
+    if ((rc = mc_aggregate_launch(h, mu_c, ss, npts, S, d_mean + m_lo, d_var + m_lo))) return rc;
+    if (d_path_wsum && (rc = path_wsum_launch(h, mu_c, d_weights, m_lo, npts, S, d_path_wsum))) return rc;
   }
   return 0;
 }

@@ -40,6 +40,12 @@ struct mfgp_ctx {
   double* d_exp_tbl;      // 256 doubles: 2^(j/256), correctly rounded on the host
   double* h_pinned;       // 64 doubles pinned
   int* h_info;            // 4 ints pinned
+  // batched objective (mfgp_lml_grad_batch): results are written by the kernel straight into mapped pinned
+  // host memory (no copy to enqueue): 16 x 16 doubles + 16 ints, and their device-side addresses
+  double* h_batch;
+  int* h_batch_info;
+  double* d_batch;
+  int* d_batch_info;
   cudaEvent_t ev[8];
   // look-ahead Cholesky: a high-priority side stream for the panel (critical-path) kernels and
   // per-panel events ordering it against the caller's stream
@@ -113,7 +119,16 @@ int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long lo
 int small_gp_launch(mfgp_ctx* h, const KParams& kp, const double* X, const double* y, int N, double diag_add,
                     double* A, double* W, double* alpha, double* d_out, int want_grad);
 int small_gp_configure(mfgp_ctx* h);
+int small_batch_configure(mfgp_ctx* h);
+int small_batch_max();
+int small_lml_batch_launch(mfgp_ctx* h, const KParams* kps, const double* diag_add, int B, const double* X,
+                           const double* y, int N, double* d_out, int* d_info, int want_grad);
 int trmm_store(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad, double* T);
+// C(lower, n x n, ld = n) -= T^T T for T (k x n, ld = ldt); n, k multiples of 128
+int syrk_tn_sub(mfgp_ctx* h, const double* T, long long ldt, int k, double* C, int n);
+// Z[i][c] = sum_{k<=i} L[i][k] E[k][c]   (L: n x n lower with explicit zeros above the diagonal inside its
+// diagonal 128-blocks; E, Z: n x ldc row-major, ldc multiple of 128)
+int trmm_right_store(mfgp_ctx* h, const double* L, int n, const double* E, long long ldc, double* Z);
 
 // ---- assemble.cu -------------------------------------------------------------------------
 int assemble_configure(mfgp_ctx* h);

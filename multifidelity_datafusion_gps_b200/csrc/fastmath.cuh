@@ -74,4 +74,34 @@ __device__ __forceinline__ double exp2s(double u, unsigned tbl) {
   return __hiloint2double(hi, __double2loint(res));
 }
 
+// Same arithmetic with a plain 256-entry table (entry j at byte 8*j of tbl_flat): for single-CTA kernels on
+// tiny problems, where staging the 32 KB bank-replicated copy costs more than the bank conflicts it avoids.
+// Bit-identical results to exp2s.
+__device__ __forceinline__ double exp2s_flat(double u, unsigned tbl_flat) {
+  const double MAGIC = 6755399441055744.0;
+  {
+    const unsigned hi = min((unsigned)__double2hiint(u), 0xC10FF000u);
+    u = __hiloint2double((int)hi, __double2loint(u));
+  }
+  const double t = u + MAGIC;
+  const int n = __double2loint(t);
+  const double f = u - (t - MAGIC);
+  double h = fma(f, 2.239395190875157e-12, 3.3083026805413713e-09);
+  h = fma(h, f, 3.6655655969101062e-06);
+  h = fma(h, f, 2.7076061740622863e-03);
+  double T;
+  asm("{\n\t.reg .u32 j, a;\n\t"
+      "and.b32 j, %1, 255;\n\t"
+      "mad.lo.u32 a, j, 8, %2;\n\t"
+      "ld.shared.f64 %0, [a];\n\t}"
+      : "=d"(T) : "r"(n), "r"(tbl_flat));
+  const double res = fma(T, h * f, T);
+  int hi;
+  asm("{\n\t.reg .u32 q;\n\t"
+      "and.b32 q, %1, 0xffffff00;\n\t"
+      "mad.lo.u32 %0, q, 4096, %2;\n\t}"
+      : "=r"(hi) : "r"(n), "r"(__double2hiint(res)));
+  return __hiloint2double(hi, __double2loint(res));
+}
+
 }  // namespace fm

@@ -274,7 +274,11 @@ __global__ void __launch_bounds__(T::THREADS, 1)
     const double* sa = smem + (f % STAGES) * T::STAGE_DOUBLES;
     const double* sb = sa + T::A_STAGE;
     const int krel = c_kt * BK - c_ti * T::BM;    // >= 0 inside the diagonal block
-    if (krel < 0) {                               // dense part of the row tile: no zero structure
+    // Inside the diagonal block only the warps whose rows straddle this k tile see zero structure: warps
+    // entirely below it (wm0 >= krel + BK) hold a dense 32-deep slab and take the fully unrolled path,
+    // warps entirely above it (wm0 + WTM <= krel) hold explicit zeros and have nothing to add.  Same
+    // products in the same order as before: bit-identical sums.
+    if (krel < 0 || wm0 >= krel + BK) {           // dense part of the row tile: no zero structure
 #pragma unroll
       for (int kk = 0; kk < BK / 4; kk++) {
         double a[T::MT], b[T::NT];
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(T::THREADS, 1)
       // occupies the tensor pipe), hence a warp-uniform computed entry into a fall-through chain.
       static_assert(T::MT <= 8, "fall-through chain below covers at most 8 row tiles per warp");
 #pragma unroll 1
-      for (int kk = 0; kk < BK / 4; kk++) {
+      for (int kk = 0; kk < (wm0 + T::WTM <= krel ? 0 : BK / 4); kk++) {
         const int imin = max(0, (krel + 4 * kk - wm0) >> 3);
         if (imin >= T::MT) break;                 // later kk only skip more
         double b[T::NT];

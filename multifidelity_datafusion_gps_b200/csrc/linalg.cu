@@ -329,6 +329,250 @@ __global__ void __launch_bounds__(256, 1)
   }
 }
 
+// ---- batched-theta objective for N <= 128: one CTA per hyper-parameter vector, only scalars come back ----
+// What the optimiser needs from an evaluation is (LML, gradient) -- not the factors.  The reference refits 5-30
+// high-fidelity points with 1 + 6 L-BFGS-B runs per adaptation step (src/abstractMFGP.py:131-137,
+// src/gpc/mfgp_gpc.py:17-20); the 6 restarts are independent, so their evaluations are batched: B vectors
+// in ONE launch (gp.GPRegression drives the restarts in lock-step).  Compared with small_gp_kernel the
+// register tile, the staging matrix and every loop are sized by NB = ceil(N / 16) at compile time, the
+// exponential uses a plain 2 KB table, and nothing N x N is written to global memory (small_gp_kernel
+// writes two full 128 x 128 matrices per evaluation whatever N is).  Same arithmetic per element.
+struct SmallTheta {
+  double uz, ux, u3, lc12, ls3, s3, diag_add, pad;
+};
+constexpr int SMALL_BATCH_MAX = 16;
+struct SmallBatch {
+  SmallTheta th[SMALL_BATCH_MAX];
+};
+
+template <int KB, int NB>
+__device__ __forceinline__ void small_fused_block(double (&t)[NB][NB], double* col0, double* col1, double* dinv,
+                                                  int tx, int ty, int* bad, int nvalid) {
+  const int kend = min(LT, nvalid - KB * LT);
+  for (int ko = 0; ko < kend; ko++) {
+    const int k = KB * LT + ko;
+    double* buf = (k & 1) ? col1 : col0;
+    if (tx == ko) {
+#pragma unroll
+      for (int a = 0; a < NB; a++) buf[ty + LT * a] = t[a][KB];
+    }
+    __syncthreads();
+    double p = buf[k];
+    if (!(p > 0.0)) {   // also catches NaN
+      if (tx == 0 && ty == 0 && bad[0] == 0) bad[0] = k + 1;
+      p = 1.0;
+    }
+    const double rinv = rsqrt(p);
+    if (tx == ko) {
+#pragma unroll
+      for (int a = KB; a < NB; a++) {
+        const int i = ty + LT * a;
+        if (i > k) t[a][KB] *= rinv;
+        else if (i == k) { t[a][KB] = p * rinv; dinv[k] = rinv; }
+      }
+    }
+    double li[NB], lj[NB], wr[NB];
+#pragma unroll
+    for (int a = KB; a < NB; a++) li[a] = buf[ty + LT * a] * rinv;
+#pragma unroll
+    for (int b = KB; b < NB; b++) lj[b] = buf[tx + LT * b] * rinv;
+#pragma unroll
+    for (int a = 0; a <= KB; a++) {
+      const int r = ty + LT * a;
+      wr[a] = (r == k) ? rinv : -rinv * buf[r];
+    }
+#pragma unroll
+    for (int a = KB; a < NB; a++) {
+      if (a == KB && ty <= ko) continue;
+#pragma unroll
+      for (int b = KB; b <= a; b++) {
+        if (b == KB && tx <= ko) continue;
+        if (a == b && tx > ty) continue;
+        t[a][b] = fma(-li[a], lj[b], t[a][b]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a <= KB; a++) {
+      if (a == KB && ty > ko) continue;
+#pragma unroll
+      for (int b = KB; b < NB; b++) {
+        if (b == KB && tx <= ko) continue;
+        t[a][b] = fma(lj[b], wr[a], t[a][b]);
+      }
+    }
+  }
+}
+
+template <int KB, int NB>
+__device__ __forceinline__ void small_eliminate(double (&t)[NB][NB], double* col0, double* col1, double* dinv,
+                                                int tx, int ty, int* bad, int nvalid) {
+  if constexpr (KB < NB) {
+    small_fused_block<KB, NB>(t, col0, col1, dinv, tx, ty, bad, nvalid);
+    small_eliminate<KB + 1, NB>(t, col0, col1, dinv, tx, ty, bad, nvalid);
+  }
+}
+
+template <int NB>
+constexpr int small_batch_smem_doubles(int D) {
+  return 256 + (NB * 16) * (NB * 16 + 1) + 6 * (NB * 16) + 64 + D * (NB * 16);
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256, 1)
+    small_lml_batch_kernel(SmallBatch params, int D, int d, const double* __restrict__ X,
+                           const double* __restrict__ y, int N, const double* __restrict__ gtbl,
+                           double* __restrict__ out /* (B, 16) */, int* __restrict__ info /* (B) */,
+                           int want_grad) {
+  constexpr int NP = NB * 16, LD = NP + 1;
+  extern __shared__ __align__(16) double sm[];
+  __shared__ int s_bad;
+  double* stbl = sm;                 // [256] 2^(j/256)
+  double* S = stbl + 256;            // [NP][LD] packed matrix
+  double* dinv = S + NP * LD;        // [NP]
+  double* sy = dinv + NP;
+  double* sv = sy + NP;
+  double* sal = sv + NP;
+  double* col0 = sal + NP;
+  double* col1 = col0 + NP;
+  double* red = col1 + NP;           // [64]
+  double* sX = red + 64;             // [D][NP]
+  const SmallTheta th = params.th[blockIdx.x];
+  const int tid = threadIdx.x, tx = tid & (LT - 1), ty = tid >> 4;
+  const int lane = tid & 31, warp = tid >> 5;
+  stbl[tid] = gtbl[tid];
+  for (int idx = tid; idx < NP * D; idx += 256) {
+    const int r = idx / D, dd = idx - r * D;
+    sX[dd * NP + r] = r < N ? X[idx] : 0.0;
+  }
+  if (tid < NP) {
+    sy[tid] = tid < N ? y[tid] : 0.0;
+    dinv[tid] = 1.0;
+  }
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  const unsigned tbl = (unsigned)__cvta_generic_to_shared(stbl);
+  const bool has3 = th.s3 != 0.0;
+  auto parts = [&](int i, int j, double& rx, double& rz, double& k12, double& k3) {
+    rx = 0.0;
+    rz = 0.0;
+    for (int dd = 0; dd < D; dd++) {
+      const double q = sX[dd * NP + i] - sX[dd * NP + j];
+      if (dd < d) rx = fma(q, q, rx);
+      else rz = fma(q, q, rz);
+    }
+    k12 = fm::exp2s_flat(fma(th.uz, rz, fma(th.ux, rx, th.lc12)), tbl);
+    k3 = has3 ? fm::exp2s_flat(fma(th.u3, rx, th.ls3), tbl) : 0.0;
+  };
+  double t[NB][NB];
+#pragma unroll
+  for (int a = 0; a < NB; a++)
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      const int i = ty + LT * a, j = tx + LT * b;
+      double v = 0.0;
+      if (j <= i) {
+        if (i < N) {
+          double rx, rz, k12, k3;
+          parts(i, j, rx, rz, k12, k3);
+          v = k12 + k3 + (i == j ? th.diag_add : 0.0);
+        } else {
+          v = (i == j) ? 1.0 : 0.0;
+        }
+      }
+      t[a][b] = v;
+    }
+  small_eliminate<0, NB>(t, col0, col1, dinv, tx, ty, &s_bad, N);
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < NB; a++)
+#pragma unroll
+    for (int b = 0; b < NB; b++) S[(ty + LT * a) * LD + tx + LT * b] = t[a][b];
+  __syncthreads();
+  // upper positions: accumulators -> W itself, S[j][i] = W[i][j] (j < i)
+  for (int idx = tid; idx < NP * NP; idx += 256) {
+    const int i = idx / NP, j = idx - i * NP;
+    if (j < i) S[j * LD + i] *= -dinv[i];
+  }
+  __syncthreads();
+  if (tid < NP) {   // v = W y
+    double acc = 0.0;
+    if (tid < N) {
+      for (int k = 0; k < tid; k++) acc = fma(S[k * LD + tid], sy[k], acc);
+      acc = fma(dinv[tid], sy[tid], acc);
+    }
+    sv[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < NP) {   // alpha = W^T v
+    double acc = 0.0;
+    if (tid < N) {
+      acc = dinv[tid] * sv[tid];
+      for (int i = tid + 1; i < N; i++) acc = fma(S[tid * LD + i], sv[i], acc);
+    }
+    sal[tid] = acc;
+  }
+  __syncthreads();
+  double* o = out + (long)blockIdx.x * 16;
+  if (warp == 0) {   // log det and y^T alpha, fixed order
+    double ld = 0.0, ya = 0.0;
+    for (int i = lane; i < N; i += 32) {
+      ld -= log(dinv[i]);
+      ya = fma(sy[i], sal[i], ya);
+    }
+#pragma unroll
+    for (int q = 16; q > 0; q >>= 1) {
+      ld += __shfl_xor_sync(0xffffffffu, ld, q);
+      ya += __shfl_xor_sync(0xffffffffu, ya, q);
+    }
+    if (lane == 0) {
+      const double logdet = 2.0 * ld;
+      o[1] = logdet;
+      o[2] = ya;
+      o[0] = 0.5 * (-(double)N * 1.8378770664093453 - logdet - ya);
+      info[blockIdx.x] = s_bad;
+    }
+  }
+  if (!want_grad) return;
+  double G6[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+  for (int a = 0; a < NB; a++) {
+    const int i = ty + LT * a;
+#pragma unroll 1
+    for (int b = 0; b <= a; b++) {
+      const int j = tx + LT * b;
+      if (j <= i && i < N) {
+        // K^-1[i][j] = sum_{k > i} W[k][i] W[k][j] + W[i][i] W[i][j]
+        double acc = dinv[i] * (j < i ? S[j * LD + i] : dinv[i]);
+        for (int k = i + 1; k < N; k++) acc = fma(S[i * LD + k], S[j * LD + k], acc);
+        double rx, rz, k12, k3;
+        parts(i, j, rx, rz, k12, k3);
+        const double wgt = (i == j) ? 0.5 : 1.0;      // G = 0.5 (aa^T - K^-1); off-diagonal counted twice
+        const double G = wgt * fma(sal[i], sal[j], -acc);
+        const double gk = G * k12, g3 = G * k3;
+        G6[0] += gk;
+        G6[1] = fma(gk, rz, G6[1]);
+        G6[2] = fma(gk, rx, G6[2]);
+        G6[3] += g3;
+        G6[4] = fma(g3, rx, G6[4]);
+        if (i == j) G6[5] += G;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    double v = G6[q];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if (lane == 0) red[warp * 6 + q] = v;
+  }
+  __syncthreads();
+  if (tid < 6) {
+    double v = 0.0;
+    for (int w = 0; w < 8; w++) v += red[w * 6 + tid];
+    o[8 + tid] = v;
+  }
+}
+
 // A/B switch for the throughput tile (environment MFGP_TILE_WARPS=8|16), read once
 int tile_variant() {
   static int v = -1;
@@ -475,6 +719,9 @@ int linalg_configure(mfgp_ctx* h) {
   rc |= configure_gemm<dg::Big, true, true>(h);
   rc |= configure_gemm<dg::Big, false, true>(h);
   rc |= configure_gemm<dg::Big, false, false>(h);
+  rc |= configure_gemm<dg::Big, true, false>(h);
+  rc |= configure_gemm<dg::Small, true, false>(h);
+  rc |= configure_gemm<dg::Big16, true, false>(h);
   rc |= configure_gemm<dg::Small, true, true>(h);
   rc |= configure_gemm<dg::Small, false, true>(h);
   rc |= configure_gemm<dg::Small, false, false>(h);
@@ -632,6 +879,21 @@ int trmm_store(mfgp_ctx* h, const double* W, int npad, const double* Ks, long lo
   return launch_gemm<true, true>(h, p, PC_MISC);
 }
 
+int syrk_tn_sub(mfgp_ctx* h, const double* T, long long ldt, int k, double* C, int n) {
+  ARG_CHECK(h, n % LEAF == 0 && k % LEAF == 0 && ldt >= n);
+  // C[i][j] -= sum_r T[r][i] * T[r][j] on the lower tiles
+  dg::GemmParams p = gp(T, ldt, T, ldt, C, n, n, n, k, -1.0, 1.0);
+  p.lower_only = 1;
+  return launch_gemm<false, false>(h, p, PC_MISC);
+}
+
+int trmm_right_store(mfgp_ctx* h, const double* L, int n, const double* E, long long ldc, double* Z) {
+  ARG_CHECK(h, n % LEAF == 0 && ldc % dg::Big::BN == 0 && ldc < (1LL << 31));
+  dg::GemmParams p = gp(L, n, E, ldc, Z, ldc, n, (int)ldc, n, 1.0, 0.0);
+  p.ke_row = 1;
+  return launch_gemm<true, false>(h, p, PC_MISC);
+}
+
 int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad,
                double* out_ss) {
   ARG_CHECK(h, npad % LEAF == 0 && cols_pad % dg::Big::BN == 0);
@@ -667,4 +929,58 @@ int small_gp_configure(mfgp_ctx* h) {
   CUDA_TRY(h, cudaFuncSetAttribute(small_gp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    SMALL_SMEM_FIXED + MFGP_MAX_D * LEAF * (int)sizeof(double)));
   return 0;
+}
+
+
+// ---- batched-theta objective (see small_lml_batch_kernel) ----------------------------------------------
+template <int NB>
+static int small_batch_run(mfgp_ctx* h, const SmallBatch& sb, int B, int D, int d, const double* X, const double* y,
+                           int N, double* d_out, int* d_info, int want_grad) {
+  const size_t smem = (size_t)small_batch_smem_doubles<NB>(D) * sizeof(double);
+  prof_begin(h, PC_LEAF);
+  small_lml_batch_kernel<NB><<<B, 256, smem, h->stream>>>(sb, D, d, X, y, N, h->d_exp_tbl, d_out, d_info, want_grad);
+  prof_end(h, PC_LEAF);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int small_batch_max() { return SMALL_BATCH_MAX; }
+
+// kps: B <= SMALL_BATCH_MAX parameter sets; diag_add[b] = noise + 1e-8 + jitter.  d_out: (B, 16) doubles,
+// [0..2] = {LML, logdet, y^T alpha}, [8..13] = the six gradient sums; d_info: (B) first bad pivot or 0.
+int small_lml_batch_launch(mfgp_ctx* h, const KParams* kps, const double* diag_add, int B, const double* X,
+                           const double* y, int N, double* d_out, int* d_info, int want_grad) {
+  ARG_CHECK(h, N >= 1 && N <= LEAF && B >= 1 && B <= SMALL_BATCH_MAX);
+  SmallBatch sb;
+  memset(&sb, 0, sizeof(sb));
+  for (int b = 0; b < B; b++) {
+    sb.th[b].uz = kps[b].uz; sb.th[b].ux = kps[b].ux; sb.th[b].u3 = kps[b].u3;
+    sb.th[b].lc12 = kps[b].lc12; sb.th[b].ls3 = kps[b].ls3; sb.th[b].s3 = kps[b].s3;
+    sb.th[b].diag_add = diag_add[b];
+  }
+  const int D = kps[0].D, d = kps[0].d;
+  switch ((N + LT - 1) / LT) {
+    case 1: return small_batch_run<1>(h, sb, B, D, d, X, y, N, d_out, d_info, want_grad);
+    case 2: return small_batch_run<2>(h, sb, B, D, d, X, y, N, d_out, d_info, want_grad);
+    case 3: return small_batch_run<3>(h, sb, B, D, d, X, y, N, d_out, d_info, want_grad);
+    case 4: return small_batch_run<4>(h, sb, B, D, d, X, y, N, d_out, d_info, want_grad);
+    case 5: return small_batch_run<5>(h, sb, B, D, d, X, y, N, d_out, d_info, want_grad);
+    case 6: return small_batch_run<6>(h, sb, B, D, d, X, y, N, d_out, d_info, want_grad);
+    case 7: return small_batch_run<7>(h, sb, B, D, d, X, y, N, d_out, d_info, want_grad);
+    default: return small_batch_run<8>(h, sb, B, D, d, X, y, N, d_out, d_info, want_grad);
+  }
+}
+
+template <int NB>
+static int small_batch_cfg(mfgp_ctx* h) {
+  CUDA_TRY(h, cudaFuncSetAttribute(small_lml_batch_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   small_batch_smem_doubles<NB>(MFGP_MAX_D) * (int)sizeof(double)));
+  return 0;
+}
+
+int small_batch_configure(mfgp_ctx* h) {
+  int rc = 0;
+  rc |= small_batch_cfg<1>(h); rc |= small_batch_cfg<2>(h); rc |= small_batch_cfg<3>(h); rc |= small_batch_cfg<4>(h);
+  rc |= small_batch_cfg<5>(h); rc |= small_batch_cfg<6>(h); rc |= small_batch_cfg<7>(h); rc |= small_batch_cfg<8>(h);
+  return rc ? -100 : 0;
 }

@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(256)
                         const double* __restrict__ alpha, const double* __restrict__ Xtest,
                         const double* __restrict__ mu_l, const double* __restrict__ sd_l,
                         const double* __restrict__ eps, unsigned long long seed, long long m_global0,
-                        long long m_lo, int S, double* __restrict__ Ks, double* __restrict__ mu_c) {
+                        long long m_lo, int S, double* __restrict__ Ks, double* __restrict__ mu_c,
+                        const double* __restrict__ zcol, long long z_off, long long ldz) {
   extern __shared__ __align__(16) double stbl_all[];   // exp table (32 KB) | zs[MC_MAXS]
   __shared__ __align__(16) double su[MC_KCHUNK], sv[MC_KCHUNK], sz[MC_KCHUNK], sa[MC_KCHUNK];
   __shared__ double macc[MC_MAXS];
@@ -214,14 +215,20 @@ __global__ void __launch_bounds__(256)
   const int d = kp.d;               // D = d + 1
   double xm[MFGP_MAX_D];
   for (int dd = 0; dd < d; dd++) xm[dd] = Xtest[m * d + dd];
-  const double mul = mu_l[m], sdl = sd_l[m];
+  const double mul = mu_l ? mu_l[m] : 0.0, sdl = sd_l ? sd_l[m] : 1.0;
   const double uz = kp.uz;
   // all S low-fidelity samples of this point up front, one thread each (Philox + Box-Muller costs a few
-  // hundred instructions: left to lane 0 of the sample's warp it stalled the other 31 lanes)
+  // hundred instructions: left to lane 0 of the sample's warp it stalled the other 31 lanes).  With zcol the
+  // samples were drawn by the caller (deeper levels of a chain, joint sampling across test points):
+  // z_s = mul + zcol[(z_off + point) * ldz + s]
   for (int s = tid; s < S; s += 256) {
     macc[s] = 0.0;
-    const double e = eps ? eps[m * S + s] : philox_normal((unsigned long long)((m_global0 + m) * S + s), seed);
-    zs[s] = fma(sdl, e, mul);
+    if (zcol) {
+      zs[s] = mul + zcol[(z_off + blockIdx.x) * ldz + s];
+    } else {
+      const double e = eps ? eps[m * S + s] : philox_normal((unsigned long long)((m_global0 + m) * S + s), seed);
+      zs[s] = fma(sdl, e, mul);
+    }
   }
   for (int k0 = 0; k0 < npad; k0 += MC_KCHUNK) {
     const int klen = min(MC_KCHUNK, npad - k0);
@@ -434,6 +441,49 @@ __global__ void mc_aggregate_kernel(const double* __restrict__ mu_c, const doubl
   }
   mean[m] = mbar;
   var[m] = sv / S + dev / S;
+}
+
+// z[c] = mu_c[c] + sqrt(v_c[c]) * eps for the columns c = (m - m_lo) * S + s of the current chunk: the sample
+// one level of a NARGP chain hands to the next (eps supplied as (M, S), or Philox counter (m_global0 + m) S + s)
+__global__ void sample_cols_kernel(const double* __restrict__ mu_c, const double* __restrict__ v_c,
+                                   const double* __restrict__ eps, unsigned long long key, long long m_global0,
+                                   long long m_lo, long long ncols, int S, double* __restrict__ z) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  const long long m = m_lo + c / S;
+  const int s = (int)(c % S);
+  const double e = eps ? eps[m * S + s] : philox_normal((unsigned long long)((m_global0 + m) * S + s), key);
+  z[c] = fma(sqrt(v_c[c]), e, mu_c[c]);
+}
+
+// E[j][s] (ld = ldE, zero padded to rows x ldE) from supplied normals (M, S) or Philox counter j * S + s
+__global__ void fill_normal_padded_kernel(const double* __restrict__ eps, unsigned long long seed, long long M,
+                                          int S, long long rows, long long ldE, double* __restrict__ E) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * ldE) return;
+  const long long j = idx / ldE;
+  const int s = (int)(idx - j * ldE);
+  double v = 0.0;
+  if (j < M && s < S) v = eps ? eps[j * S + s] : philox_normal((unsigned long long)(j * S + s), seed);
+  E[idx] = v;
+}
+
+// path[s] += sum_m w[m_lo + m] * mu_c[m * S + s] over the points of one chunk; one block per sample path,
+// fixed-order reduction, chunks arrive in stream order: deterministic
+__global__ void __launch_bounds__(256)
+    path_wsum_kernel(const double* __restrict__ mu_c, const double* __restrict__ w, long long m_lo,
+                     long long npts, int S, double* __restrict__ path) {
+  __shared__ double sv[256];
+  const int s = blockIdx.x;
+  double acc = 0.0;
+  for (long long m = threadIdx.x; m < npts; m += 256) acc = fma(w ? w[m_lo + m] : 1.0, mu_c[m * S + s], acc);
+  sv[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sv[threadIdx.x] += sv[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) path[s] += sv[0];
 }
 
 // ---- deterministic reductions -----------------------------------------------------------------
@@ -718,12 +768,13 @@ int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, 
                         const double* alpha, const double* Xtest, const double* mu_l,
                         const double* sd_l, const double* eps, unsigned long long seed,
                         long long m_global0, long long m_lo, long long npts, int S,
-                        long long cols_pad, double* Ks, double* mu_c) {
+                        long long cols_pad, double* Ks, double* mu_c, const double* zcol, long long z_off,
+                        long long ldz) {
   if (npts <= 0) return 0;
   ARG_CHECK(h, S <= MC_MAXS);
   prof_begin(h, PC_CROSSGEN);
   cross_gen_mc_kernel<<<(unsigned)npts, 256, fm::EXP_TBL_BYTES + MC_MAXS * sizeof(double), h->stream>>>(
-      kp, X, N, npad, alpha, Xtest, mu_l, sd_l, eps, seed, m_global0, m_lo, S, Ks, mu_c);
+      kp, X, N, npad, alpha, Xtest, mu_l, sd_l, eps, seed, m_global0, m_lo, S, Ks, mu_c, zcol, z_off, ldz);
   prof_end(h, PC_CROSSGEN);
   LAUNCH_CHECK(h);
   const long long tail = (cols_pad - npts * S) * npad;
@@ -867,6 +918,31 @@ int wdot_launch(mfgp_ctx* h, const double* w, const double* x, long long n, doub
   wdot_stage1_kernel<<<nb, 256, 0, h->stream>>>(w, x, n, h->d_partials);
   LAUNCH_CHECK(h);
   sum_stage2_kernel<<<1, 256, 0, h->stream>>>(h->d_partials, nb, d_out);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int sample_cols_launch(mfgp_ctx* h, const double* mu_c, const double* v_c, const double* eps,
+                       unsigned long long key, long long m_global0, long long m_lo, long long ncols, int S,
+                       double* z) {
+  if (ncols <= 0) return 0;
+  sample_cols_kernel<<<nblk(ncols, 256), 256, 0, h->stream>>>(mu_c, v_c, eps, key, m_global0, m_lo, ncols, S, z);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int fill_normal_padded_launch(mfgp_ctx* h, const double* eps, unsigned long long seed, long long M, int S,
+                              long long rows, long long ldE, double* E) {
+  if (rows * ldE <= 0) return 0;
+  fill_normal_padded_kernel<<<nblk(rows * ldE, 256), 256, 0, h->stream>>>(eps, seed, M, S, rows, ldE, E);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int path_wsum_launch(mfgp_ctx* h, const double* mu_c, const double* w, long long m_lo, long long npts, int S,
+                     double* path) {
+  if (npts <= 0 || S <= 0) return 0;
+  path_wsum_kernel<<<S, 256, 0, h->stream>>>(mu_c, w, m_lo, npts, S, path);
   LAUNCH_CHECK(h);
   return 0;
 }

@@ -11,6 +11,7 @@ SciPy's L-BFGS-B on the host, exactly as paramz does it; its objective is one GP
 No CPU fallback: constructing a model without a visible B200 raises ``MfgpError``.
 """
 import ctypes
+import os
 import re
 import threading
 
@@ -18,7 +19,7 @@ import numpy as np
 import torch
 from scipy import optimize as _sopt
 
-from . import _ffi
+from . import _ffi, _lbfgsb
 from ._ffi import TILE, KIND_COMPOSITE, KIND_RBF, MfgpError, NotPositiveDefinite, padded_n
 
 _LIM_VAL = 36.0
@@ -149,6 +150,24 @@ def to_device(arr, device):
     return t.to("cuda:%d" % device, non_blocking=False)
 
 
+SMALL_BATCH_N = 128      # mfgp_lml_grad_batch: one CTA per hyper-parameter vector
+
+
+def _small_batch_enabled():
+    """MFGP_SMALL_BATCH=0 routes the optimiser's objective through mfgp_lml_grad (A/B and parity checks)."""
+    return os.environ.get("MFGP_SMALL_BATCH", "1") != "0"
+
+
+def _fast_lbfgsb_enabled():
+    """MFGP_FAST_LBFGSB=0: always go through scipy.optimize.fmin_l_bfgs_b's own Python wrapper."""
+    return os.environ.get("MFGP_FAST_LBFGSB", "1") != "0"
+
+
+def _lockstep_enabled():
+    """MFGP_LOCKSTEP=0: optimize_restarts runs its restarts one after the other (the reference's loop)."""
+    return os.environ.get("MFGP_LOCKSTEP", "1") != "0"
+
+
 class GPRegression:
     """GPy.models.GPRegression look-alike running on one B200."""
 
@@ -264,6 +283,26 @@ class GPRegression:
         self._a_holds_L = False                     # d_A now holds K^-1
         return lml.value, np.array([grad[i] for i in range(P)])
 
+    def lml_and_grad_batch(self, thetas, want_grad=True, handle=None):
+        """B hyper-parameter vectors (B, P) -> (lml (B,), grad (B, P), info (B,)) in ONE launch, one CTA per
+        vector (mfgp_lml_grad_batch; N <= 128).  Nothing but scalars comes back: the posterior of this
+        model is NOT updated.  info[b] > 0: the factorisation of vector b met a non-positive pivot
+        (evaluate it through ``lml_and_grad``, which replays the jitter schedule)."""
+        assert self.N <= SMALL_BATCH_N, "the batched objective serves N <= %d" % SMALL_BATCH_N
+        h = handle if handle is not None else _ffi.get_handle(self.device)
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64).reshape(-1, len(self.names))
+        B, P = thetas.shape
+        lml = np.empty(B)
+        grad = np.empty((B, P))
+        info = np.zeros(B, dtype=np.int32)
+        vp = ctypes.c_void_p
+        h.check(h.lib.mfgp_lml_grad_batch(
+            h.h, self.kern.kind, self._dX.data_ptr(), self._dy.data_ptr(), self.N, self.D, self.kern.d,
+            thetas.ctypes.data_as(vp), P, B, 0.0, lml.ctypes.data_as(vp),
+            grad.ctypes.data_as(vp) if want_grad else None, info.ctypes.data_as(vp)))
+        self.n_evals += B
+        return lml, grad, info
+
     def _ensure_posterior(self):
         if not self._dirty:
             return
@@ -338,6 +377,12 @@ class GPRegression:
         return self._lml
 
     # -- paramz optimisation -----------------------------------------------------------------
+    @staticmethod
+    def _feasible(theta):
+        # a line search that left the representable range (NaN, or a softplus that underflowed to 0) is an
+        # infeasible point like a failed factorisation (paramz counts both as failures)
+        return bool(np.all(np.isfinite(theta)) and np.all(theta[:-1] > 0.0) and theta[-1] >= 0.0)
+
     def _objective_grads(self, x):
         """paramz Model._objective_grads over the transformed, un-fixed parameters."""
         free = ~self._fixed
@@ -345,11 +390,15 @@ class GPRegression:
         theta[free] = logexp_f(x)
         self._set_params(theta)
         try:
-            # a line search that left the representable range (NaN, or a softplus that underflowed to 0)
-            # is an infeasible point like a failed factorisation (paramz counts both as failures)
-            if not (np.all(np.isfinite(theta)) and np.all(theta[:-1] > 0.0) and theta[-1] >= 0.0):
+            if not self._feasible(theta):
                 raise NotPositiveDefinite(0)
-            lml, g = self.lml_and_grad(theta)
+            if getattr(self, "N", SMALL_BATCH_N + 1) <= SMALL_BATCH_N and _small_batch_enabled():
+                # the reference's own sizes: scalars-only kernel (no factors written; the posterior is
+                # rebuilt once, after the optimiser has finished)
+                lml_b, g_b, info = self.lml_and_grad_batch(theta[None, :])
+                lml, g = (float(lml_b[0]), g_b[0]) if info[0] == 0 else self.lml_and_grad(theta)
+            else:
+                lml, g = self.lml_and_grad(theta)
             if not (np.isfinite(lml) and np.all(np.isfinite(g))):
                 raise NotPositiveDefinite(0)
             self._fail_count = 0
@@ -360,11 +409,22 @@ class GPRegression:
             return np.inf, np.zeros(int(free.sum()))
         return -lml, -(g[free] * logexp_gradfactor(theta[free]))
 
+    def _minimise(self, fun, x0, max_iters):
+        """scipy.optimize.fmin_l_bfgs_b(fun, x0, maxfun=max_iters, maxiter=max_iters) as paramz's opt_lbfgsb
+        calls it -- through the stepped driver around the same compiled routine when it reproduces SciPy's
+        iterates bit for bit on this installation (_lbfgsb.selfcheck), else through SciPy's own wrapper."""
+        if _fast_lbfgsb_enabled() and _lbfgsb.selfcheck():
+            return _lbfgsb.minimize(fun, x0, maxfun=max_iters, maxiter=max_iters)
+        return _sopt.fmin_l_bfgs_b(fun, x0, maxfun=max_iters, maxiter=max_iters)
+
     def optimize(self, optimizer=None, max_iters=1000, messages=False, **kw):
         free = ~self._fixed
         x0 = logexp_finv(self.param_array[free])
-        x_opt, f_opt, _ = _sopt.fmin_l_bfgs_b(self._objective_grads, x0, maxfun=max_iters,
-                                               maxiter=max_iters)
+        x_opt, _, _ = self._minimise(self._objective_grads, x0, max_iters)
+        # paramz opt_lbfgsb.opt: self.f_opt = f_fp(self.x_opt)[0] -- the objective is evaluated once more at the
+        # returned point (after an abnormal line-search exit SciPy's own f is the last TRIAL point's), and
+        # that value is what optimize_restarts compares  [paramz-recall]
+        f_opt = self._objective_grads(np.array(x_opt, dtype=np.float64))[0]
         theta = self.param_array
         theta[free] = logexp_f(x_opt)
         self._set_params(theta)
@@ -382,6 +442,15 @@ class GPRegression:
         rank, world = dist.rank_world()
         if parallel and world > 1:
             return self._optimize_restarts_distributed(num_restarts, robust, rank, world, **kwargs)
+        if self._lockstep_ok(num_restarts):
+            starts = [None] + [np.random.normal(size=int(free.sum())) for _ in range(1, num_restarts)]
+            runs = self._optimize_lockstep(list(range(num_restarts)), starts, robust, **kwargs)
+            self.optimization_runs.extend((x, f) for _, f, x in runs)
+            if runs:
+                theta = self.param_array
+                theta[free] = logexp_f(dist.best_run(runs)[2])
+                self._set_params(theta)
+            return self
         for i in range(num_restarts):
             try:
                 if i > 0:
@@ -414,7 +483,11 @@ class GPRegression:
         starts = [None] + [np.random.normal(size=nfree) for _ in range(1, num_restarts)]
         theta0 = self.param_array.copy()
         local = []
-        for i in dist.restart_share(num_restarts, rank, world):
+        share = dist.restart_share(num_restarts, rank, world)
+        if self._lockstep_ok(len(share)):
+            local = self._optimize_lockstep(share, starts, robust, **kwargs)     # this rank's share, batched
+            share = []
+        for i in share:
             try:
                 theta = theta0.copy()
                 if i > 0:
@@ -433,6 +506,151 @@ class GPRegression:
             theta[free] = logexp_f(dist.best_run(runs)[2])
         self._set_params(theta)
         return self
+
+    def _lockstep_ok(self, n_runs):
+        return (n_runs > 1 and getattr(self, "N", SMALL_BATCH_N + 1) <= SMALL_BATCH_N
+                and _small_batch_enabled() and _lockstep_enabled())
+
+    def _objective_batch(self, thetas, free, handle=None):
+        """[(objective, gradient over the free transformed parameters) or None] for full hyper-parameter
+        vectors, ONE batched launch for the feasible ones (mfgp_lml_grad_batch, one CTA each).  None =
+        infeasible point / failed factorisation (paramz counts both as failures).  A vector whose
+        factorisation met a non-positive pivot is re-evaluated through lml_and_grad, which replays GPy's
+        jitter schedule."""
+        thetas = np.asarray(thetas, dtype=np.float64).reshape(-1, len(self.names))
+        ok = np.array([self._feasible(th) for th in thetas], dtype=bool)
+        out = [None] * len(thetas)
+        if ok.any():
+            lml, grad, info = self.lml_and_grad_batch(thetas[ok], handle=handle)
+            for b, l, g, bad in zip(np.flatnonzero(ok), lml, grad, info):
+                if bad != 0:
+                    try:
+                        l, g = self.lml_and_grad(thetas[b])
+                    except NotPositiveDefinite:
+                        continue
+                if np.isfinite(l) and np.all(np.isfinite(g)):
+                    out[b] = (-float(l), -(g[free] * logexp_gradfactor(thetas[b][free])))
+        return out
+
+    def _optimize_lockstep(self, indices, starts, robust, max_iters=1000, **_):
+        """The restarts `indices` of optimize_restarts (src/abstractMFGP.py:137) on ONE GPU in lock-step:
+        every run is its own L-BFGS-B instance (_lbfgsb.LbfgsbRun: SciPy's compiled step, resumable at
+        every objective evaluation); each round, the points at which the still running instances want the
+        objective are evaluated by ONE batched launch (one CTA per run).  An evaluation depends on nothing
+        but its own hyper-parameters, so every run follows exactly the trajectory it follows in the serial
+        loop (same starts: run 0 from the current point, run i > 0 from starts[i], drawn by the caller in the
+        serial order).  Returns [(index, objective at x_opt, x_opt)]."""
+        if not (_fast_lbfgsb_enabled() and _lbfgsb.selfcheck()):
+            return self._optimize_lockstep_threads(indices, starts, robust, max_iters)
+        free = ~self._fixed
+        nfree = int(free.sum())
+        base = self.param_array.copy()
+
+        def theta_of(x):
+            theta = base.copy()
+            theta[free] = logexp_f(x)
+            return theta
+        runs = {i: _lbfgsb.LbfgsbRun(logexp_finv(base[free]) if starts[i] is None
+                                     else logexp_finv(logexp_f(starts[i])), max_iters, max_iters) for i in indices}
+        fails = {i: 0 for i in indices}
+        errors = {}
+        while True:
+            want = [i for i in indices if i not in errors and runs[i].advance()]
+            if not want:
+                break
+            vals = self._objective_batch([theta_of(runs[i].x) for i in want], free)
+            for i, v in zip(want, vals):
+                if v is None:
+                    if fails[i] >= 10:                     # paramz: more than ten failures in a row re-raise
+                        errors[i] = NotPositiveDefinite(0)
+                        continue
+                    fails[i] += 1
+                    runs[i].supply(np.inf, np.zeros(nfree))
+                else:
+                    fails[i] = 0
+                    runs[i].supply(*v)
+        self._dirty = True
+        if errors and not robust:
+            raise errors[min(errors)]
+        done = [i for i in indices if i not in errors]
+        # paramz opt_lbfgsb.opt: f_opt = f_fp(x_opt)[0], for all runs in one more batched launch
+        final = self._objective_batch([theta_of(runs[i].x) for i in done], free) if done else []
+        return [(i, (v[0] if v is not None else np.inf), np.array(runs[i].x, dtype=np.float64))
+                for i, v in zip(done, final)]
+
+    def _optimize_lockstep_threads(self, indices, starts, robust, max_iters=1000):
+        """Fallback when SciPy's compiled step cannot be driven directly: every run is a
+        ``fmin_l_bfgs_b`` call in its own thread; their objective calls meet in a rendezvous and are
+        evaluated by one batched launch per round.  Same trajectories as the serial loop."""
+        free = ~self._fixed
+        nfree = int(free.sum())
+        base = self.param_array.copy()
+        handle = _ffi.get_handle(self.device)          # the calling thread's handle serves every batch
+        cv = threading.Condition()
+        pending, results, errors, finished = {}, {}, {}, {}
+        live = [len(indices)]
+
+        def flush():                                   # under cv, by the thread that completes the round
+            tids = sorted(pending)
+            thetas = [pending[t] for t in tids]
+            pending.clear()
+            try:
+                vals = self._objective_batch(thetas, free, handle=handle)
+            except BaseException as exc:               # a CUDA / argument failure fails every waiting run
+                vals = [exc] * len(tids)
+            results.update(zip(tids, vals))
+            cv.notify_all()
+
+        def evaluate(tid, theta):
+            with cv:
+                pending[tid] = theta
+                if len(pending) == live[0]:
+                    flush()
+                while tid not in results:
+                    cv.wait()
+                res = results.pop(tid)
+            if isinstance(res, BaseException):
+                raise res
+            return res
+
+        def retire():
+            with cv:
+                live[0] -= 1
+                if pending and len(pending) == live[0]:
+                    flush()
+
+        def run(i):
+            fails = [0]
+
+            def fun(x):
+                theta = base.copy()
+                theta[free] = logexp_f(x)
+                res = evaluate(i, theta)
+                if res is None:
+                    if fails[0] >= 10:
+                        raise NotPositiveDefinite(0)
+                    fails[0] += 1
+                    return np.inf, np.zeros(nfree)
+                fails[0] = 0
+                return res
+            try:
+                x0 = logexp_finv(base[free]) if starts[i] is None else logexp_finv(logexp_f(starts[i]))
+                x_opt, _, _ = _sopt.fmin_l_bfgs_b(fun, x0, maxfun=max_iters, maxiter=max_iters)
+                finished[i] = (i, fun(x_opt)[0], np.asarray(x_opt, dtype=np.float64))      # paramz: f_fp(x_opt)[0]
+            except BaseException as exc:
+                errors[i] = exc
+            finally:
+                retire()
+
+        threads = [threading.Thread(target=run, args=(i,), daemon=True) for i in indices]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        self._dirty = True
+        if errors and not robust:
+            raise errors[min(errors)]
+        return [finished[i] for i in sorted(finished)]
 
     # -- prediction ----------------------------------------------------------------------------
     def level_struct(self):

@@ -7,8 +7,12 @@ kernel on [x, mu_{t-1}(x)] -- whose low-fidelity function is the posterior mean 
 chains the package's own ``NARGP`` objects that way; every level's mean is evaluated on the GPU and handed
 to the next level through the ``device_predict`` hook of ``MultifidelityDataFusion._augment_device``.
 """
-import numpy as np
+import ctypes
 
+import numpy as np
+import torch
+
+from .. import _ffi, gp
 from ._presets import NARGP
 
 
@@ -70,3 +74,50 @@ class MultiLevelNARGP:
     def predict_level(self, t, X_test):
         """Prediction of fidelity level t (2 .. L)."""
         return self.models[t - 2].predict(X_test)
+
+    # -- Monte-Carlo propagation through every level -------------------------------------------------
+    def predict_mc_device(self, dX, n_samples=100, d_eps=None, seed=0, m0=0, d_weights=None,
+                          include_lower_noise=True):
+        """Sample-based propagation through ALL levels (Perdikaris et al. 2017, section 2(c)): per sample,
+        z_1 ~ N(mu_1(x), v_1(x)) at level 1, then (mu_t, v_t) = level t at [x, z_{t-1}] and
+        z_t ~ N(mu_t, v_t) up the chain; mean = mean_s mu_L, var = mean_s v_L + var_s mu_L.
+        dX (M, d) CUDA -> (mean (M,), var (M,), weighted sum or None).  d_eps: optional (L-1, M, S) standard
+        normals; otherwise Philox (one key per level, counter = global point index * S + sample, so shards
+        with m0 reproduce the full batch).  With two levels this is NARGP.predict_mc."""
+        top = self.models[-1]
+        h = _ffi.get_handle(top.device)
+        gps = [self.models[0].lf_model] + [m.hf_model for m in self.models]
+        for m in self.models:
+            m._apply_add_noise()
+        structs = [g.level_struct() for g in gps]
+        L = len(structs)
+        ptrs = (ctypes.c_void_p * L)(*[ctypes.addressof(st) for st in structs])
+        M, S = int(dX.shape[0]), int(n_samples)
+        mean = torch.empty(M, dtype=torch.float64, device=dX.device)
+        var = torch.empty(M, dtype=torch.float64, device=dX.device)
+        wsum = ctypes.c_double(0.0) if d_weights is not None else None
+        nph = max(g.npad for g in gps[1:])
+        per_col = (nph + self.input_dim + 4) * 8
+        need = 16 * M + max((S + 256) * per_col, (gps[0].npad + 1) * 128 * 8) + 4096
+        ws = gp.workspace(top.device, max(min(16 * M + 148 * 128 * 4 * per_col, 12 << 30), need))
+        h.check(h.lib.mfgp_predict_mc_chain(
+            h.h, ctypes.cast(ptrs, ctypes.c_void_p), L, dX.data_ptr(), M, S,
+            d_eps.data_ptr() if d_eps is not None else None, int(seed), int(m0), int(include_lower_noise), 1,
+            d_weights.data_ptr() if d_weights is not None else None, mean.data_ptr(), var.data_ptr(),
+            ctypes.byref(wsum) if wsum is not None else None, ws.data_ptr(), ws.numel() * 8))
+        return mean, var, (wsum.value if wsum is not None else None)
+
+    def predict_mc(self, X_test, n_samples=100, eps=None, seed=0, weights=None, m0=0, include_lower_noise=True):
+        """NumPy front end of predict_mc_device: (mean (M,1), var (M,1)); eps: optional (L-1, M, S)."""
+        X_test = np.ascontiguousarray(X_test, dtype=np.float64)
+        assert X_test.ndim == 2 and X_test.shape[1] == self.input_dim
+        dev = self.models[-1].device
+        d_eps = None
+        if eps is not None:
+            eps = np.asarray(eps, dtype=np.float64).reshape(len(self.models), X_test.shape[0], n_samples)
+            d_eps = gp.to_device(eps, dev)
+        d_w = gp.to_device(np.asarray(weights).ravel(), dev) if weights is not None else None
+        mean, var, wsum = self.predict_mc_device(gp.to_device(X_test, dev), n_samples, d_eps, seed, m0, d_w,
+                                                 include_lower_noise)
+        self.last_pce_mean = wsum
+        return mean.cpu().numpy()[:, None], var.cpu().numpy()[:, None]

@@ -289,6 +289,9 @@ class OracleGPRegression:
         x0 = logexp_finv(self.theta[free])
         x_opt, f_opt, info = sopt.fmin_l_bfgs_b(self.objective_and_grad, x0,
                                                maxfun=max_iters, maxiter=max_iters)
+        # paramz opt_lbfgsb.opt: self.f_opt = f_fp(self.x_opt)[0] -- re-evaluated at the returned point; this
+        # is the value optimize_restarts compares  [paramz-recall]
+        f_opt = self.objective_and_grad(x_opt)[0]
         self.theta[free] = logexp_f(x_opt)
         self._post = None
         return x_opt, f_opt

@@ -189,6 +189,47 @@ class OracleMFGP:
         return mean, var
 
 
+    def predict_mc_joint(self, X_test, eps, include_lf_noise=True, jitter=0.0):
+        """MC propagation with the LF posterior sampled JOINTLY across the test points (E = 1):
+        Sigma = K_l(X*, X*) - tmp^T tmp (+ noise I, + jitter I), z_s = mu_l + chol(Sigma) eps[:, s];
+        eps (M, S).  Returns (mean (M,1), var (M,1), mu_s (M,S))."""
+        assert self.offsets.shape[0] == 1
+        lf = self.lf_model
+        L, alpha = lf.posterior()
+        theta_k, noise = go.split_theta(lf.kind, lf.theta)
+        mu, _, tmp = go.posterior_predict(lf.kind, lf.X, lf.d, lf.theta, L, alpha, X_test,
+                                          include_noise=False, form=self.form, return_tmp=True)
+        Sigma = go.kernel_K(lf.kind, X_test, None, lf.d, theta_k, "direct") - tmp.T.dot(tmp)
+        Sigma[np.diag_indices(X_test.shape[0])] += (noise if include_lf_noise else 0.0) + jitter
+        z = mu + np.linalg.cholesky(Sigma).dot(eps)                         # (M, S)
+        M, S = eps.shape
+        Xa = np.concatenate([np.repeat(X_test[:, None, :], S, axis=1), z[:, :, None]], axis=2)
+        mu_s, v_s = self.hf_model.predict(Xa.reshape(M * S, -1))
+        mu_s, v_s = mu_s.reshape(M, S), v_s.reshape(M, S)
+        return (mu_s.mean(axis=1, keepdims=True), v_s.mean(axis=1, keepdims=True) + mu_s.var(axis=1, keepdims=True),
+                mu_s)
+
+
+def predict_mc_chain(levels, X_test, eps, include_lower_noise=True):
+    """MC propagation through a chain of GP levels (recursive NARGP; Perdikaris et al. 2017, sec. 2(c)):
+    levels[0] a GP on x, levels[t >= 1] GPs on [x, z].  eps (L-1, M, S) standard normals:
+    z_1 = mu_0 + sd_0 eps_1; (mu_t, v_t) = level t at [x, z_t]; z_{t+1} = mu_t + sqrt(v_t) eps_{t+1};
+    mean = mean_s mu_top, var = mean_s v_top + var_s(mu_top).  levels: OracleGPRegression objects."""
+    Lm1, M, S = eps.shape
+    assert Lm1 == len(levels) - 1
+    mu, v = levels[0].predict(X_test, include_noise=include_lower_noise)     # (M,1)
+    z = mu + np.sqrt(v) * eps[0]                                             # (M,S)
+    Xrep = np.repeat(X_test[:, None, :], S, axis=1)
+    for t in range(1, len(levels)):
+        top = t == len(levels) - 1
+        Xa = np.concatenate([Xrep, z[:, :, None]], axis=2).reshape(M * S, -1)
+        mu_s, v_s = levels[t].predict(Xa, include_noise=True if top else include_lower_noise)
+        mu_s, v_s = mu_s.reshape(M, S), v_s.reshape(M, S)
+        if not top:
+            z = mu_s + np.sqrt(v_s) * eps[t]
+    return mu_s.mean(axis=1, keepdims=True), v_s.mean(axis=1, keepdims=True) + mu_s.var(axis=1, keepdims=True)
+
+
 # --------------------------------------------------------------------------------------
 # A9: candidate-set acquisition
 # --------------------------------------------------------------------------------------

@@ -206,7 +206,9 @@ def test_lf_level_optimize_reaches_oracle_likelihood(pkg):
         o = go.OracleGPRegression(lf_X, lf_Y)
         o.optimize()
         ours, theirs = m.lf_model.log_likelihood(), o.log_likelihood()
-        assert ours >= theirs - 1e-6 * abs(theirs) - 1e-3, (dim, ours, theirs)
+        # both runs stop on a flat, ill-conditioned ridge (noise -> 1e-13): the oracle's own two distance forms
+        # end 2.4e-6 apart on the 1-D curve, hence 1e-5 and not 1e-6
+        assert ours >= theirs - 1e-5 * abs(theirs) - 1e-3, (dim, ours, theirs)
         theta = m.lf_model.param_array
         cond = np.linalg.cond(go.assemble_Ky(go.KIND_RBF, lf_X, dim, theta, form="direct"))
         chk = go.inference(go.KIND_RBF, lf_X, lf_Y, dim, theta, want_grad=False, form="direct")
@@ -713,3 +715,105 @@ def test_three_level_nargp_recursion_matches_oracle_chain(pkg):
     assert util.rel_err(mean, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.2) < 1e-6
     mean2, _ = ml.predict_level(2, Xt)
     assert util.rel_err(mean2, o2.predict(Xt)[0]) < 1e-8
+
+
+def test_lockstep_restarts_equal_the_serial_loop(pkg, monkeypatch):
+    """optimize_restarts (src/abstractMFGP.py:137) with the six restarts in lock-step on one GPU (one batched
+    launch per round of evaluations) must end where the reference's serial loop ends: same runs, same
+    objectives, same winner, bit for bit -- for the composite and the plain kernel."""
+    _, X_hf, _ = _data(2, n_hf=14)
+    for cls, args in ((pkg.GPDF, (2, 0.001, 2)), (pkg.NARGP, (2,))):
+        out = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("MFGP_LOCKSTEP", mode)
+            np.random.seed(3)
+            m = cls(*args, util.hf_2d, util.lf_2d)
+            m.fit(X_hf)
+            out[mode] = (m.hf_model.param_array.copy(), [f for _, f in m.hf_model.optimization_runs],
+                         [x.copy() for x, _ in m.hf_model.optimization_runs], m.predict(X_hf[:3]))
+        assert np.array_equal(out["0"][0], out["1"][0])
+        assert out["0"][1] == out["1"][1] and len(out["1"][1]) == 7
+        assert all(np.array_equal(a, b) for a, b in zip(out["0"][2], out["1"][2]))
+        assert np.array_equal(out["0"][3][0], out["1"][3][0])
+
+
+def _three_levels(pkg):
+    from multifidelity_datafusion_gps_b200.models import MultiLevelNARGP
+    rs = np.random.RandomState(13)
+    X1, X2, X3 = rs.uniform(size=(80, 2)), rs.uniform(size=(30, 2)), rs.uniform(size=(12, 2))
+    f1 = lambda x: util.lf_2d(x) + 0.3 * np.cos(4 * x[:, :1])
+    Y1, Y2, Y3 = f1(X1), util.lf_2d(X2), util.hf_2d(X3)
+    lf_theta = np.array([1.5, 0.4, 1e-3])
+    ml = MultiLevelNARGP(2, [X1, X2, X3], [Y1, Y2, Y3]).fit(thetas=[THETA_C, THETA_C], lf_theta=lf_theta)
+    o2 = mo.OracleMFGP(2, 0, 0, lambda X: Y2, lf_X=X1, lf_Y=Y1, lf_theta=lf_theta)
+    o2.fit(X2, theta=THETA_C)
+    o3 = mo.OracleMFGP(2, 0, 0, lambda X: Y3, f_low=lambda x: o2.predict(x)[0])
+    o3.fit(X3, theta=THETA_C)
+    return ml, [o2.lf_model, o2.hf_model, o3.hf_model], rs
+
+
+def test_mc_propagation_through_three_levels(pkg):
+    # SURVEY.md section 8f rank 4: samples (not means) travel up the chain level 1 -> 2 -> 3
+    from multifidelity_datafusion_gps_b200 import ops
+    ml, levels, rs = _three_levels(pkg)
+    M, S = 300, 48
+    Xt = rs.uniform(size=(M, 2))
+    eps = np.random.default_rng(6).standard_normal((2, M, S))
+    mean, var = ml.predict_mc(Xt, n_samples=S, eps=eps)
+    mu_ref, var_ref = mo.predict_mc_chain(levels, Xt, eps)
+    assert util.rel_err(mean, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.2) < 1e-6
+    # zero normals collapse every level to its mean: the mean-propagating predict()
+    mean0, var0 = ml.predict_mc(Xt, n_samples=1, eps=np.zeros((2, M, 1)))
+    mu, v = ml.predict(Xt)
+    assert util.rel_err(mean0, mu) < 1e-12 and util.rel_err(var0, v, 1.2) < 1e-10
+    # in-kernel Philox: level 1 -> 2 draws the keys of mfgp_predict_mc, level 2 -> 3 its own key; a shard with
+    # m0 reproduces the rows of the full batch
+    seed = 9
+    mean_p, var_p = ml.predict_mc(Xt, n_samples=S, seed=seed)
+    e1 = ops.fill_normal(seed, 0, M * S, "cuda:0").cpu().numpy().reshape(M, S)
+    e2 = ops.fill_normal((seed + 0x9E3779B97F4A7C15) % (1 << 64), 0, M * S, "cuda:0").cpu().numpy().reshape(M, S)
+    mu_ref, var_ref = mo.predict_mc_chain(levels, Xt, np.stack([e1, e2]))
+    assert util.rel_err(mean_p, mu_ref) < 1e-8 and util.rel_err(var_p, var_ref, 1.2) < 1e-6
+    mean_s, var_s = ml.predict_mc(Xt[100:], n_samples=S, seed=seed, m0=100)
+    assert np.array_equal(mean_s, mean_p[100:]) and np.array_equal(var_s, var_p[100:])
+    # two levels through the chain entry point == NARGP.predict_mc, bit for bit
+    from multifidelity_datafusion_gps_b200.models import MultiLevelNARGP
+    two = MultiLevelNARGP(2, ml.level_X[:2], ml.level_Y[:2]).fit(thetas=[THETA_C], lf_theta=np.array([1.5, 0.4, 1e-3]))
+    a = two.predict_mc(Xt, n_samples=S, seed=seed)
+    b = two.models[0].predict_mc(Xt, n_samples=S, seed=seed)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_mc_with_joint_lf_sampling_across_test_points(pkg):
+    # SURVEY.md section 8f rank 4, "full-covariance LF sampling for small M": z_s = mu_l + chol(Sigma_l) eps_s
+    # with the M x M low-fidelity predictive covariance; per-path functionals come back too
+    m, o = _mc_models(pkg, n_l=100, n_h=30, d=4, seed=4)
+    for M, S in ((200, 64), (130, 33)):
+        Xt = np.random.default_rng(M).uniform(size=(M, 4))
+        w = np.random.default_rng(M + 1).uniform(size=M)
+        w /= w.sum()
+        eps = np.random.default_rng(M + 2).standard_normal((M, S))
+        mean, var = m.predict_mc(Xt, n_samples=S, eps=eps, weights=w, joint=True)
+        mu_ref, var_ref, mu_s = o.predict_mc_joint(Xt, eps)
+        assert util.rel_err(mean, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.1) < 1e-6
+        paths_ref = (w[:, None] * mu_s).sum(axis=0)
+        assert util.rel_err(m.last_pce_paths, paths_ref) < 1e-8
+        assert np.isclose(m.last_pce_mean, paths_ref.mean(), rtol=1e-10)
+    # in-kernel Philox (counter m*S + s) and extra jitter
+    from multifidelity_datafusion_gps_b200 import ops
+    M, S, seed = 150, 40, 12
+    Xt = np.random.default_rng(77).uniform(size=(M, 4))
+    mean, var = m.predict_mc(Xt, n_samples=S, seed=seed, joint=True, lf_jitter=1e-5)
+    eps = ops.fill_normal(seed, 0, M * S, "cuda:0").cpu().numpy().reshape(M, S)
+    mu_ref, var_ref, _ = o.predict_mc_joint(Xt, eps, jitter=1e-5)
+    assert util.rel_err(mean, mu_ref) < 1e-8 and util.rel_err(var, var_ref, 1.1) < 1e-6
+    # the marginal statistics agree with independent-marginal sampling in expectation (same marginals):
+    # with S large the two estimates of the mean are close
+    S2 = 1000
+    a, _ = m.predict_mc(Xt[:40], n_samples=S2, seed=1, joint=True)
+    b, _ = m.predict_mc(Xt[:40], n_samples=S2, seed=2)
+    assert np.max(np.abs(a - b)) < 0.05 * max(1.0, np.max(np.abs(b)))
+    # duplicate test points make Sigma_l singular without noise: reported, not silently wrong
+    Xd = np.vstack([Xt[:20], Xt[:1]])
+    with pytest.raises(np.linalg.LinAlgError):
+        m.predict_mc(Xd, n_samples=8, seed=1, joint=True, include_lf_noise=False)

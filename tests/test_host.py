@@ -220,3 +220,45 @@ def test_restart_parallel_fit_world_size_2_gloo_equals_serial():
     for rank, theta, objs in res:
         assert np.array_equal(theta, serial.param_array)              # same winner, bit for bit
         assert objs == [f for _, f in serial.optimization_runs]       # same runs, in run order
+
+
+# ---- the stepped L-BFGS-B driver must be SciPy's optimiser, bit for bit --------------------------------------
+def test_stepped_lbfgsb_reproduces_scipy_bit_for_bit():
+    """gp.GPRegression drives SciPy's compiled L-BFGS-B step directly (no ScalarFunction layers; resumable
+    at every evaluation so that independent restarts can share one batched GPU launch).  Its iterates must
+    equal scipy.optimize.fmin_l_bfgs_b's (what paramz calls) on smooth, failing (+inf) and budget-limited
+    runs; otherwise the package falls back to fmin_l_bfgs_b (selfcheck)."""
+    from scipy import optimize as sopt
+    from multifidelity_datafusion_gps_b200 import _lbfgsb as lb
+    assert lb.selfcheck()
+
+    def make(seed):
+        rng = np.random.default_rng(seed)
+        A = rng.standard_normal((7, 7))
+        Q, b = A @ A.T + 0.1 * np.eye(7), rng.standard_normal(7)
+
+        def f(x):
+            if np.abs(x).max() > 6.0:
+                return np.inf, np.zeros(7)
+            return float(0.5 * x @ Q @ x - b @ x + np.sum(np.sin(2 * x))), Q @ x - b + 2 * np.cos(2 * x)
+        return f
+    for seed in range(12):
+        f = make(seed)
+        x0 = 2.0 * np.random.default_rng(100 + seed).standard_normal(7)
+        for budget in (1000, 15, 5):
+            a = sopt.fmin_l_bfgs_b(f, x0, maxfun=budget, maxiter=budget)
+            b = lb.minimize(f, x0, maxfun=budget, maxiter=budget)
+            assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+            assert (a[2]["funcalls"], a[2]["nit"], a[2]["warnflag"]) == (b[2]["funcalls"], b[2]["nit"], b[2]["warnflag"])
+    f = make(0)
+    x0s = [np.random.default_rng(200 + s).standard_normal(7) for s in range(6)]
+    calls = []
+
+    def batch(xs):
+        calls.append(len(xs))
+        return [f(x) for x in xs]
+    res = lb.minimize_lockstep(batch, x0s, 1000, 1000)
+    for (x, fx, info), x0 in zip(res, x0s):
+        a = sopt.fmin_l_bfgs_b(f, x0, maxfun=1000, maxiter=1000)
+        assert np.array_equal(x, a[0]) and fx == a[1] and info["funcalls"] == a[2]["funcalls"]
+    assert calls[0] == 6 and sum(calls) == sum(r[2]["funcalls"] for r in res)    # one batch per round
