@@ -770,7 +770,9 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                                     "sample": sample, "seconds": dt}
             if not args.no_extras:
-                line["cpu_baseline"]["per_row_reference_loop"] = per_row_reference_loop(wl, 1024)
+                # 32 rows (~8 s): one reference-style row costs ~0.25 s at N_l = 4096 (every call copies the
+                # 134 MB factor for dtrtrs), so M = 1024 rows would take more than four minutes
+                line["cpu_baseline"]["per_row_reference_loop"] = per_row_reference_loop(wl, 32)
         if world == 1 and not args.no_extras:
             del model
             gp.release_workspaces()
