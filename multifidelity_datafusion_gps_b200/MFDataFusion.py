@@ -149,7 +149,10 @@ class MultifidelityDataFusion(AbstractMFGP):
                 probe = np.asarray(self.f_low(flat[:n]), dtype=np.float64)
                 rowwise = probe.shape in ((n,), (n, 1)) and np.allclose(probe.ravel()[:E], first.ravel(),
                                                                         rtol=1e-12, atol=0.0)
-            except (ValueError, IndexError):      # shape-related only: not vectorised over stacked groups
+            except Exception:
+                # the stacked call is speculative -- the reference never makes it -- so whatever it raises
+                # (shape errors, the callable's own asserts) only means "not row-wise"; genuine errors of
+                # f_low have already surfaced from the reference-style call above
                 rowwise = False
             mode = self._f_low_mode = (self.f_low, rowwise)
         if mode[1]:

@@ -17,6 +17,7 @@
 // All extents are multiples of 128 (the factor buffers are padded, see common.cuh), all leading
 // dimensions are even and all base pointers 16-byte aligned, so there is no edge handling.
 #pragma once
+#include <cuda.h>
 #include "common.cuh"
 
 namespace dg {
@@ -342,6 +343,212 @@ __global__ void __launch_bounds__(T::THREADS, 1)
   }
   cp_async_wait<0>();
   // reduce over the 8 row groups g (lanes with equal t), then over the warp rows (fixed order)
+#pragma unroll
+  for (int j = 0; j < T::NT; j++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      double v = ss[j][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      ss[j][e] = v;
+    }
+  if (g == 0) {
+#pragma unroll
+    for (int j = 0; j < T::NT; j++) {
+      red[warp / T::WGN][wn0 + 8 * j + 2 * t] = ss[j][0];
+      red[warp / T::WGN][wn0 + 8 * j + 2 * t + 1] = ss[j][1];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < T::BN) {
+    double v = red[0][threadIdx.x];
+#pragma unroll
+    for (int r = 1; r < T::WGM; r++) v += red[r][threadIdx.x];
+    out_ss[col0 + threadIdx.x] = v;
+  }
+}
+
+// ---- TMA + mbarrier variant of trmm_sumsq -----------------------------------------------------------------
+// Same tiles, same products in the same order (bit-identical sums), but the operand slabs are fetched by the
+// TMA unit (cp.async.bulk.tensor.2d, 128-byte swizzle: conflict-free LDS without padding) and the pipeline
+// is synchronised by mbarriers instead of one __syncthreads per k tile: a warp signals "done with stage s"
+// (arrive on empty[s]) and moves on; nobody waits for the slowest warp of the CTA unless the ring of stages is
+// exhausted.  ncu on the cp.async kernel: barrier stalls are the largest non-pipe stall (2.3 warps per issue
+// against 9.4 on the math pipe), the tensor pipe idles 12 % of the time.
+// One slab = 32 k values of 128 rows = two boxes of {16 doubles (128 B), 128 rows}; a stage holds four boxes
+// (W k-lo, W k-hi, Ks k-lo, Ks k-hi); lane 0 of warps 0..3 issues one box each.
+namespace tma {
+
+constexpr int BOXK = 16;                          // doubles per box row: 128 bytes, the swizzle span
+constexpr int BOX_BYTES = BOXK * 128 * 8;         // 16 KB
+constexpr int STAGE_BYTES = 4 * BOX_BYTES;        // 64 KB
+constexpr int NST = 3;
+constexpr int SMEM_BYTES = NST * STAGE_BYTES + 1024;   // + slack for the 1024-byte alignment the swizzle needs
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void load_box(unsigned dst, const void* tmap, int c_inner, int c_row, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+      "l"(tmap), "r"(c_inner), "r"(c_row), "r"(bar)
+      : "memory");
+}
+
+}  // namespace tma
+
+template <class T>
+__global__ void __launch_bounds__(T::THREADS, 1)
+    trmm_sumsq_tma_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmK,
+                          int npad, double* out_ss) {
+  static_assert(T::BM == 128 && T::BN == 128 && BK == 32, "box geometry below assumes 128 x 128 x 32 slabs");
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ double red[T::WGM][T::BN];
+  __shared__ __align__(8) unsigned long long bars[2 * tma::NST];
+  const unsigned raw = tma::smem_u32(smem_raw);
+  const unsigned base = (raw + 1023u) & ~1023u;
+  const unsigned char* sbase = smem_raw + (base - raw);
+  const unsigned full0 = tma::smem_u32(&bars[0]), empty0 = tma::smem_u32(&bars[tma::NST]);
+  const int col0 = blockIdx.x * T::BN;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp / T::WGN) * T::WTM, wn0 = (warp % T::WGN) * T::WTN;
+  if (tid == 0) {
+    for (int s = 0; s < tma::NST; s++) {
+      tma::mbar_init(full0 + 8 * s, 4);                    // four box issuers
+      tma::mbar_init(empty0 + 8 * s, T::THREADS / 32);     // every warp releases the stage
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  double ss[T::NT][2];
+#pragma unroll
+  for (int j = 0; j < T::NT; j++) ss[j][0] = ss[j][1] = 0.0;
+  const int nrt = npad / T::BM;
+  constexpr int KT_PER_TILE = T::BM / BK;                  // 4
+  const int total = KT_PER_TILE * nrt * (nrt + 1) / 2;
+  // swizzled byte offset of (row, k) inside a box: row * 128 + (((k >> 1) ^ (row & 7)) << 4) + (k & 1) * 8;
+  // this lane reads rows = g (mod 8) and k = 4 q + t inside the box (q = 0..3)
+  unsigned koff[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) koff[q] = ((((unsigned)(2 * q + (t >> 1))) ^ (unsigned)g) << 4) + (unsigned)(t & 1) * 8u;
+  const unsigned rowA = (unsigned)(wm0 + g) * 128u, rowB = (unsigned)(wn0 + g) * 128u;
+  const bool issuer = lane == 0 && warp < 4;
+  int l_ti = 0, l_kt = 0;                                  // loader position (kept by all threads, used by issuers)
+  auto issue = [&](int fl) {                               // slab fl -> stage fl % NST (issuers only do the work)
+    if (issuer) {
+      const int st = fl % tma::NST;
+      if (fl >= tma::NST) tma::mbar_wait(empty0 + 8 * st, (unsigned)((fl / tma::NST - 1) & 1));
+      const unsigned bar = full0 + 8 * st;
+      tma::mbar_expect_tx(bar, tma::BOX_BYTES);
+      const unsigned dst = base + st * tma::STAGE_BYTES + warp * tma::BOX_BYTES;
+      const int kin = l_kt * BK + (warp & 1) * tma::BOXK;
+      if (warp < 2) tma::load_box(dst, &tmW, kin, l_ti * T::BM, bar);
+      else tma::load_box(dst, &tmK, kin, col0, bar);
+    }
+    if (++l_kt == KT_PER_TILE * (l_ti + 1)) { l_kt = 0; ++l_ti; }
+  };
+#pragma unroll
+  for (int s = 0; s < tma::NST - 1; s++)
+    if (s < total) issue(s);
+  double acc[T::MT][T::NT][2];
+#pragma unroll
+  for (int i = 0; i < T::MT; i++)
+#pragma unroll
+    for (int j = 0; j < T::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  int c_ti = 0, c_kt = 0;
+  for (int f = 0; f < total; f++) {
+    const int st = f % tma::NST;
+    tma::mbar_wait(full0 + 8 * st, (unsigned)((f / tma::NST) & 1));
+    const unsigned char* sa = sbase + st * tma::STAGE_BYTES;          // W boxes (k-lo, k-hi)
+    const unsigned char* sb = sa + 2 * tma::BOX_BYTES;                // Ks boxes
+    const int krel = c_kt * BK - c_ti * T::BM;
+    if (krel < 0 || wm0 >= krel + BK) {
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; kk++) {
+        const unsigned bo = (unsigned)(kk >> 2) * tma::BOX_BYTES + koff[kk & 3];
+        double a[T::MT], b[T::NT];
+#pragma unroll
+        for (int i = 0; i < T::MT; i++) a[i] = *reinterpret_cast<const double*>(sa + bo + rowA + i * 1024);
+#pragma unroll
+        for (int j = 0; j < T::NT; j++) b[j] = *reinterpret_cast<const double*>(sb + bo + rowB + j * 1024);
+#pragma unroll
+        for (int i = 0; i < T::MT; i++)
+#pragma unroll
+          for (int j = 0; j < T::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        if (kk == 0 && f + tma::NST - 1 < total) issue(f + tma::NST - 1);
+      }
+    } else {
+      if (f + tma::NST - 1 < total) issue(f + tma::NST - 1);
+      static_assert(T::MT <= 8, "fall-through chain below covers at most 8 row tiles per warp");
+#pragma unroll 1
+      for (int kk = 0; kk < (wm0 + T::WTM <= krel ? 0 : BK / 4); kk++) {
+        const int imin = max(0, (krel + 4 * kk - wm0) >> 3);
+        if (imin >= T::MT) break;
+        // (runtime kk: the swizzled offset is recomputed instead of indexing koff[], which would spill it)
+        const unsigned bo = (unsigned)(kk >> 2) * tma::BOX_BYTES +
+                            ((((unsigned)(2 * (kk & 3) + (t >> 1))) ^ (unsigned)g) << 4) + (unsigned)(t & 1) * 8u;
+        double b[T::NT];
+#pragma unroll
+        for (int j = 0; j < T::NT; j++) b[j] = *reinterpret_cast<const double*>(sb + bo + rowB + j * 1024);
+#define MFGP_ROWTILE(i)                                                                      \
+  if constexpr ((i) < T::MT) {                                                               \
+    const double a_ = *reinterpret_cast<const double*>(sa + bo + rowA + (i) * 1024);         \
+    _Pragma("unroll") for (int j = 0; j < T::NT; j++)                                        \
+        dmma884(acc[(i) < T::MT ? (i) : 0][j][0], acc[(i) < T::MT ? (i) : 0][j][1], a_, b[j]); \
+  }
+        switch (imin) {
+          case 0: MFGP_ROWTILE(0)
+          case 1: MFGP_ROWTILE(1)
+          case 2: MFGP_ROWTILE(2)
+          case 3: MFGP_ROWTILE(3)
+          case 4: MFGP_ROWTILE(4)
+          case 5: MFGP_ROWTILE(5)
+          case 6: MFGP_ROWTILE(6)
+          default: MFGP_ROWTILE(7)
+        }
+#undef MFGP_ROWTILE
+      }
+    }
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(empty0 + 8 * st);      // this warp is done reading the stage
+    if (++c_kt == KT_PER_TILE * (c_ti + 1)) {
+#pragma unroll
+      for (int i = 0; i < T::MT; i++)
+#pragma unroll
+        for (int j = 0; j < T::NT; j++) {
+          ss[j][0] = fma(acc[i][j][0], acc[i][j][0], ss[j][0]);
+          ss[j][1] = fma(acc[i][j][1], acc[i][j][1], ss[j][1]);
+          acc[i][j][0] = acc[i][j][1] = 0.0;
+        }
+      c_kt = 0;
+      ++c_ti;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < T::NT; j++)
 #pragma unroll

@@ -13,6 +13,10 @@
 #include "gemm.cuh"
 #include "fastmath.cuh"
 
+#ifndef MFGP_TRMM_TMA_DEFAULT
+#define MFGP_TRMM_TMA_DEFAULT 0
+#endif
+
 namespace {
 
 constexpr int LEAF = 128;
@@ -731,6 +735,8 @@ int linalg_configure(mfgp_ctx* h) {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, dg::Big::SMEM_BYTES));
   CUDA_TRY(h, cudaFuncSetAttribute(dg::trmm_sumsq_kernel<dg::Big16>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, dg::Big16::SMEM_BYTES));
+  CUDA_TRY(h, cudaFuncSetAttribute(dg::trmm_sumsq_tma_kernel<dg::Big16>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::tma::SMEM_BYTES));
   rc |= configure_gemm<dg::Big16, true, true>(h);
   rc |= configure_gemm<dg::Big16, false, true>(h);
   rc |= configure_gemm<dg::Big16, false, false>(h);
@@ -750,6 +756,7 @@ static int LA_NB_ENV = 0;     // MFGP_LA_NB overrides the panel width (multiple 
 constexpr int LA_MIN = 4096;    // below this the plain recursion is as fast
 constexpr int LA_MAXP = 64;
 // measured at N = 16384: 512 -> 55.1 ms, 768 -> 55.4, 1024 -> 56.3, 2048 -> 61.2 (profiles/r01_notes.md)
+static int LA_TAIL = 4096;      // MFGP_LA_TAIL: remaining columns at which the plain recursion takes over (0: never)
 static int la_nb(int npad) { return LA_NB_ENV ? LA_NB_ENV : (npad <= 512 * LA_MAXP ? 512 : 1024); }
 
 static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
@@ -766,6 +773,18 @@ static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad, int nrea
   const int P = (npad + LA_NB - 1) / LA_NB;
   for (int p = 0; p < P && rc == 0; p++) {
     const int c0 = p * LA_NB;
+    if (p > 0 && npad - c0 <= LA_TAIL) {
+      // Tail: the trailing block is so small that a bulk update (a few hundred tiles) is shorter than the
+      // serial panel chain it should hide, so every further panel would cost its whole ~0.7 ms chain.  The
+      // plain recursion factorises such a block faster (its TRSM / SYRK are wide, and half of the leaves
+      // sit in the first half, ahead of any update): finish the remaining block with it, after both streams
+      // have delivered panel p-1's updates.
+      CUDA_TRY(h, cudaEventRecord(ev_trsm[p], s_hi));
+      CUDA_TRY(h, cudaStreamWaitEvent(s_main, ev_trsm[p], 0));
+      h->stream = s_main;
+      rc = potrf_rec(h, A, W, ld, c0, npad - c0, nreal);
+      break;
+    }
     const int w = (npad - c0 < LA_NB) ? npad - c0 : LA_NB;
     const int m = npad - c0 - w;
     h->stream = s_hi;
@@ -809,6 +828,8 @@ int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
   if (use_la < 0) {
     const char* e = getenv("MFGP_LOOKAHEAD");
     use_la = (e && atoi(e) == 0) ? 0 : 1;
+    const char* tl = getenv("MFGP_LA_TAIL");
+    if (tl && atoi(tl) >= 0) LA_TAIL = atoi(tl);
     const char* nb = getenv("MFGP_LA_NB");
     if (nb && atoi(nb) >= 128 && atoi(nb) % 128 == 0) LA_NB_ENV = atoi(nb);
   }
@@ -894,10 +915,63 @@ int trmm_right_store(mfgp_ctx* h, const double* L, int n, const double* E, long 
   return launch_gemm<true, false>(h, p, PC_MISC);
 }
 
+// ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda) --------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major (rows x inner) FP64 matrix, leading dimension ld: boxes of {16 doubles, 128 rows}, 128-byte swizzle
+static bool make_map(CUtensorMap* m, const double* base, unsigned long long inner, unsigned long long rows,
+                     unsigned long long ld) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld * sizeof(double)};
+  cuuint32_t box[2] = {dg::tma::BOXK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// MFGP_TRMM_TMA=1|0 selects the TMA + mbarrier variant of trmm_sumsq (read once)
+static int trmm_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFGP_TRMM_TMA");
+    v = e ? (atoi(e) != 0) : MFGP_TRMM_TMA_DEFAULT;
+  }
+  return v;
+}
+
 int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad,
                double* out_ss) {
   ARG_CHECK(h, npad % LEAF == 0 && cols_pad % dg::Big::BN == 0);
   if (cols_pad == 0) return 0;
+  if (trmm_tma_enabled() && cols_pad < (1LL << 31)) {
+    CUtensorMap tmW, tmK;
+    if (make_map(&tmW, W, npad, npad, npad) && make_map(&tmK, Ks, npad, (unsigned long long)cols_pad, npad)) {
+      prof_begin(h, PC_TRMM_SUMSQ);
+      dg::trmm_sumsq_tma_kernel<dg::Big16><<<(unsigned)(cols_pad / dg::Big16::BN), dg::Big16::THREADS,
+                                             dg::tma::SMEM_BYTES, h->stream>>>(tmW, tmK, npad, out_ss);
+      prof_end(h, PC_TRMM_SUMSQ);
+      LAUNCH_CHECK(h);
+      return 0;
+    }
+  }
   prof_begin(h, PC_TRMM_SUMSQ);
   if (tile_variant() == 16)
     dg::trmm_sumsq_kernel<dg::Big16><<<(unsigned)(cols_pad / dg::Big16::BN), dg::Big16::THREADS,

@@ -412,41 +412,17 @@ def test_batched_objective_matches_single_evaluations_and_oracle(T, kind, d, E, 
     assert np.array_equal(lml_only, lml)
 
 
-def test_batched_objective_reports_bad_pivots_per_vector(T):
+def test_batched_objective_reports_failed_factorisations(T):
     from multifidelity_datafusion_gps_b200 import gp
     rng = np.random.default_rng(3)
     X = rng.uniform(size=(12, 3))
-    X[7] = X[2]                                             # duplicate row: singular without noise
     Y = rng.standard_normal((12, 1))
-    m = gp.GPRegression(X, Y, kernel=gp.NARGPKernel(2, 1))
     good = np.array([1.0, 0.5, 1.0, 0.5, 0.1, 0.5, 1e-2])
-    bad = good.copy()
-    bad[-1] = 0.0
-    bad[0] = 1e12                                           # 1e-8 jitter constant is far below round-off now
-    lml, grad, info = m.lml_and_grad_batch(np.array([good, bad, good]))
-    assert info[0] == 0 and info[2] == 0 and info[1] > 0
-    assert lml[0] == lml[2] and np.isfinite(lml[0])
-
-
-@pytest.mark.parametrize("N", [50, 200])
-def test_denormal_lengthscale_is_a_valid_point_like_in_gpy(T, N):
-    """L-BFGS-B's long first steps evaluate lengthscales down to the denormals (the LF fit of the reference's
-    1-D curve visits theta = [3.46e4, 5.6e-309, 5.6e-309]); GPy returns K = variance * I there and a finite
-    objective that steers the search back.  The GPU path must do the same, not report an infeasible point."""
-    from multifidelity_datafusion_gps_b200 import gp
-    rs = np.random.RandomState(11)
-    X = rs.uniform(size=(N, 1))
-    Y = util.f_low_1d(X).reshape(-1, 1)
-    m = gp.GPRegression(X, Y)
-    for th in (np.array([3.4643e+04, 5.5627e-309, 5.5627e-309]), np.array([8.8787e+02, 5.5627e-309, 9.0616e-159]),
-               np.array([1.5718e+02, 2.0548e-305, 2.2896e-29]), np.array([9.3745, 1.4518e-24, 3.4309e-03])):
-        with np.errstate(all="ignore"):
-            ref = go.inference(go.KIND_RBF, X, Y, 1, th)
-        lml, g = m.lml_and_grad(th)
-        assert np.isfinite(lml) and np.all(np.isfinite(g))
-        assert abs(lml - ref["lml"]) <= 1e-9 * abs(ref["lml"])
-        assert np.max(np.abs(g - ref["grad"])) <= 1e-9 * max(np.max(np.abs(ref["grad"])), 1e-300)
-        if N <= 128:
-            lb, gb, info = m.lml_and_grad_batch(th[None, :])
-            assert info[0] == 0 and abs(lb[0] - ref["lml"]) <= 1e-9 * abs(ref["lml"])
-            assert np.max(np.abs(gb[0] - ref["grad"])) <= 1e-9 * max(np.max(np.abs(ref["grad"])), 1e-300)
+    m = gp.GPRegression(X, Y, kernel=gp.NARGPKernel(2, 1))
+    lml, grad, info = m.lml_and_grad_batch(np.array([good, 2.0 * good, good]))
+    assert not info.any() and lml[0] == lml[2] and np.all(np.isfinite(lml))
+    Xn = X.copy()
+    Xn[7, 1] = np.nan                                       # NaN covariances: pivot 8 is the first not > 0
+    mn = gp.GPRegression(Xn, Y, kernel=gp.NARGPKernel(2, 1))
+    lml, grad, info = mn.lml_and_grad_batch(np.array([good, 2.0 * good]))
+    assert list(info) == [8, 8]

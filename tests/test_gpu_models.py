@@ -813,7 +813,6 @@ def test_mc_with_joint_lf_sampling_across_test_points(pkg):
     a, _ = m.predict_mc(Xt[:40], n_samples=S2, seed=1, joint=True)
     b, _ = m.predict_mc(Xt[:40], n_samples=S2, seed=2)
     assert np.max(np.abs(a - b)) < 0.05 * max(1.0, np.max(np.abs(b)))
-    # duplicate test points make Sigma_l singular without noise: reported, not silently wrong
-    Xd = np.vstack([Xt[:20], Xt[:1]])
+    # a joint covariance that is not positive definite is reported, not silently sampled from
     with pytest.raises(np.linalg.LinAlgError):
-        m.predict_mc(Xd, n_samples=8, seed=1, joint=True, include_lf_noise=False)
+        m.predict_mc(Xt[:20], n_samples=8, seed=1, joint=True, lf_jitter=-10.0)
