@@ -149,6 +149,20 @@ size_t mfgp_predict_ws_bytes(int N, long long cols);
 int mfgp_predict(mfgp_handle_t h, const mfgp_level_t* gp, const double* d_Xnew, long long M,
                  double* d_mean, double* d_var, int include_noise, double* d_ws, size_t ws_bytes);
 
+/* K6, latency path: M <= mfgp_predict_small_max_rows() query rows given in HOST memory, results to HOST memory,
+ * one or two launches and ONE synchronisation (query rows and results travel through pinned host memory
+ * mapped into the device).  This is what a single objective evaluation of the reference's default acquisition
+ * costs: scipydirect calls model_predict(x[None]) up to 20 000 times in sequence
+ * (src/adaptation_maximizers/scipydirect_wrapper.py:22-26), each an __augment_Data + hf_model.predict
+ * (src/MFDataFusion.py:153-156).  hf->N <= 2048.  lf == NULL: h_X holds augmented rows (M, hf->D).
+ * lf != NULL (data-driven low fidelity): h_X holds plain inputs (M, lf->D) and the rows are augmented with
+ * the LF posterior mean at x + o_e tau first (h_offsets: HOST (E, lf->D), hf->D == lf->D + E).
+ * Same formulas as mfgp_predict; the summation orders differ, so results agree to round-off, not bit for bit. */
+int mfgp_predict_small_max_rows(void);
+int mfgp_predict_small(mfgp_handle_t h, const mfgp_level_t* hf, const mfgp_level_t* lf, const double* h_X,
+                       int M, const double* h_offsets, int E, double tau, int include_noise, double* h_mean,
+                       double* h_var);
+
 /* A1 with a data-driven low-fidelity level.  Replaces __augment_Data (src/MFDataFusion.py:177-208)
  * when f_low is lf_model.predict(.)[0] (src/abstractMFGP.py:104):
  * Xaug[i] = [x_i, mu_l(x_i + o_0 tau), ..., mu_l(x_i + o_{E-1} tau)].  h_offsets: HOST (E, d). */

@@ -21,6 +21,11 @@ class ScipyDirectMaximizer(AbstractMaximizer):
         from scipy.optimize import direct
         bound = [(lower_bound[i], upper_bound[i]) for i in range(len(lower_bound))]
 
+        # a model of this package evaluates single points through its latency path (one launch, one sync)
+        owner = getattr(model_predict, "__self__", None)
+        if owner is not None and getattr(model_predict, "__name__", "") == "predict" and hasattr(owner, "predict_point"):
+            model_predict = owner.predict_point
+
         def acquisition_curve(x):
             _, uncertainty = model_predict(np.asarray(x)[None])
             return -float(np.asarray(uncertainty).ravel()[0])

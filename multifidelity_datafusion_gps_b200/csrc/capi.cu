@@ -48,6 +48,10 @@ int build_mc_rows_joint_launch(mfgp_ctx* h, const double* Xtest, const double* m
                                const double* eps, unsigned long long seed, long long m_global0,
                                long long m_lo, long long ncols, int S, int d, int E, double* out);
 int wdot_launch(mfgp_ctx* h, const double* w, const double* x, long long n, double* d_out);
+int predict_small_max_n();
+int predict_small_launch(mfgp_ctx* h, const KParams& kh, const mfgp_level_t* hf, const KParams* kl,
+                         const mfgp_level_t* lf, const double* Xq, int M, const double* d_offs, int E, double tau,
+                         double* Xaug_tmp, double noise_add, double* out);
 
 #define JITTER_CONST 1e-8   // GPy exact_gaussian_inference.py: diag.add(Ky, variance + 1e-8)
 #define MFGP_SMALL 4096
@@ -538,6 +542,42 @@ int mfgp_predict(mfgp_handle_t h, const mfgp_level_t* gp, const double* d_Xnew, 
   return predict_impl(h, gp, kp, d_Xnew, M, d_mean, d_var, include_noise, d_ws, ws_bytes);
 }
 
+int mfgp_predict_small_max_rows(void) { return 16; }
+
+int mfgp_predict_small(mfgp_handle_t h, const mfgp_level_t* hf, const mfgp_level_t* lf, const double* h_X,
+                       int M, const double* h_offsets, int E, double tau, int include_noise, double* h_mean,
+                       double* h_var) {
+  ENTER(h);
+  KParams kh, kl;
+  int rc;
+  if ((rc = level_kparams(h, hf, &kh))) return rc;
+  ARG_CHECK(h, hf->d_W != nullptr && h_X && h_mean && h_var && M >= 1 && M <= mfgp_predict_small_max_rows());
+  ARG_CHECK(h, hf->N <= predict_small_max_n());
+  // staging in the mapped pinned block (16 x 16 doubles): [0, 128) query rows, [128, 160) results,
+  // [160, 224) augmented rows are kept on the device side of d_scalars instead (no host visibility needed)
+  const int width = lf ? lf->D : hf->D;
+  ARG_CHECK(h, M * width <= 128 && M * hf->D <= 1024);
+  double* d_offs = h->d_scalars + 64;
+  double* d_aug = h->d_scalars + 2048;
+  if (lf) {
+    if ((rc = level_kparams(h, lf, &kl))) return rc;
+    ARG_CHECK(h, h_offsets && E >= 1 && E <= MFGP_MAX_E && hf->D == lf->D + E && E * lf->D <= 96);
+    // the offsets travel as kernel-visible data through the same mapped block (after the query rows)
+    memcpy(h->h_batch + 160, h_offsets, (size_t)E * lf->D * sizeof(double));
+    d_offs = h->d_batch + 160;
+  }
+  memcpy(h->h_batch, h_X, (size_t)M * width * sizeof(double));
+  if ((rc = predict_small_launch(h, kh, hf, lf ? &kl : nullptr, lf, h->d_batch, M, d_offs, E, tau, d_aug,
+                                 include_noise ? kh.noise : 0.0, h->d_batch + 128)))
+    return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  for (int m = 0; m < M; m++) {
+    h_mean[m] = h->h_batch[128 + 2 * m];
+    h_var[m] = h->h_batch[128 + 2 * m + 1];
+  }
+  return 0;
+}
+
 int mfgp_augment(mfgp_handle_t h, const mfgp_level_t* lf, const double* d_X, long long M,
                  const double* h_offsets, int E, double tau, double* d_Xaug, double* d_ws,
                  size_t ws_bytes) {
@@ -610,11 +650,14 @@ static int mc_chain_impl(mfgp_ctx* h, const mfgp_level_t* const* levels, int L, 
   // the trmm_sumsq / cross_gen classes hold the high-fidelity launches only)
   const int prof_saved = h->prof_on;
   h->prof_on = 0;
+  static const bool trace = getenv("MFGP_TRACE_MC") != nullptr;   // stage times to stderr (diagnostics)
+  if (trace) cudaEventRecord(h->ev[0], h->stream);
   rc = predict_impl(h, lf, kp[0], d_Xtest, M, mu_l, sd_l, include_lower_noise, rest,
                     (size_t)restd * sizeof(double));
   h->prof_on = prof_saved;
   if (rc) return rc;
   if ((rc = sqrt_launch(h, sd_l, M))) return rc;
+  if (trace) cudaEventRecord(h->ev[1], h->stream);
   // upper levels over (point, sample) columns
   const int D = d + 1;
   const long long per_col = (long long)npad_max + D + 3;
@@ -662,6 +705,15 @@ static int mc_chain_impl(mfgp_ctx* h, const mfgp_level_t* const* levels, int L, 
       if ((rc = finish_var_launch(h, ss, ncols, kp[t].kdiag, with_noise ? kp[t].noise : 0.0, ss))) return rc;
     }
     if ((rc = mc_aggregate_launch(h, mu_c, ss, npts, S, d_mean + m_lo, d_var + m_lo))) return rc;
+  }
+  if (trace) {
+    cudaEventRecord(h->ev[2], h->stream);
+    cudaEventSynchronize(h->ev[2]);
+    float lf_ms = 0.f, hf_ms = 0.f;
+    cudaEventElapsedTime(&lf_ms, h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&hf_ms, h->ev[1], h->ev[2]);
+    fprintf(stderr, "[mfgp trace] predict_mc M=%lld S=%d: lowest level %.2f ms, upper levels %.2f ms\n", M, S, lf_ms,
+            hf_ms);
   }
   if (h_wsum) {
     if ((rc = wdot_launch(h, d_weights, d_mean, M, h->d_scalars + 20))) return rc;

@@ -575,4 +575,139 @@ __global__ void __launch_bounds__(T::THREADS, 1)
   }
 }
 
+// ---- TMA + mbarrier variant of gemm_kernel for k-contiguous operands (NT products) -------------------------
+// C[m][n] (+)= alpha * sum_k A[m][k] * B[n][k] with both operands row-major / k contiguous: every GEMM of the
+// Cholesky factorisation (SYRK, TRSM updates, look-ahead), the second product of the triangular inverse and
+// trmm_store.  Same tiles and accumulation order as gemm_kernel<T, true, true> (bit-identical results); the
+// slabs arrive by TMA into 128-byte-swizzled boxes and the stages are handed over by mbarriers (see
+// trmm_sumsq_tma_kernel).  The tensor maps describe the operand views starting at p.A / p.B; a batch node b
+// adds b * batch_rows to both coordinates.
+struct GemmTmaParams {
+  double* C;
+  long ldc;
+  int M, N, K;
+  double alpha, beta;
+  int lower_only;
+  int kb_row, kb_col, ke_row;
+  int batch;
+  long c_batch_stride;     // elements between the C blocks of consecutive nodes
+  int a_batch_rows, a_batch_k, b_batch_rows, b_batch_k;   // coordinate shifts per node
+};
+
+template <class T>
+__global__ void __launch_bounds__(T::THREADS, 1)
+    gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    GemmTmaParams p) {
+  static_assert(T::BM == 128 && T::BN == 128 && BK == 32, "box geometry assumes 128 x 128 x 32 slabs");
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * tma::NST];
+  const unsigned raw = tma::smem_u32(smem_raw);
+  const unsigned base = (raw + 1023u) & ~1023u;
+  const unsigned char* sbase = smem_raw + (base - raw);
+  const unsigned full0 = tma::smem_u32(&bars[0]), empty0 = tma::smem_u32(&bars[tma::NST]);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp / T::WGN) * T::WTM, wn0 = (warp % T::WGN) * T::WTN;
+  int ti, tj, node = 0;
+  int bid = blockIdx.x;
+  if (p.batch > 1) {
+    const int per_node = gridDim.x / p.batch;
+    node = bid / per_node;
+    bid %= per_node;
+  }
+  if (p.lower_only) {
+    int tt = bid;
+    ti = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
+    while ((long)(ti + 1) * (ti + 2) / 2 <= tt) ti++;
+    while ((long)ti * (ti + 1) / 2 > tt) ti--;
+    tj = tt - ti * (ti + 1) / 2;
+  } else {
+    const int tiles_n = p.N / T::BN;
+    ti = bid / tiles_n;
+    tj = bid % tiles_n;
+  }
+  const int row0 = ti * T::BM, col0 = tj * T::BN;
+  int kb = 0, ke = p.K;
+  if (p.kb_row) kb = max(kb, row0);
+  if (p.kb_col) kb = max(kb, col0);
+  if (p.ke_row) ke = min(ke, row0 + T::BM);
+  const int nk = ke > kb ? (ke - kb) / BK : 0;
+  if (tid == 0) {
+    for (int s = 0; s < tma::NST; s++) {
+      tma::mbar_init(full0 + 8 * s, 4);
+      tma::mbar_init(empty0 + 8 * s, T::THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  unsigned koff[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) koff[q] = ((((unsigned)(2 * q + (t >> 1))) ^ (unsigned)g) << 4) + (unsigned)(t & 1) * 8u;
+  const unsigned rowA = (unsigned)(wm0 + g) * 128u, rowB = (unsigned)(wn0 + g) * 128u;
+  const bool issuer = lane == 0 && warp < 4;
+  const int a_r = row0 + node * p.a_batch_rows, a_k = node * p.a_batch_k;
+  const int b_r = col0 + node * p.b_batch_rows, b_k = node * p.b_batch_k;
+  auto issue = [&](int fl) {
+    if (issuer) {
+      const int st = fl % tma::NST;
+      if (fl >= tma::NST) tma::mbar_wait(empty0 + 8 * st, (unsigned)((fl / tma::NST - 1) & 1));
+      const unsigned bar = full0 + 8 * st;
+      tma::mbar_expect_tx(bar, tma::BOX_BYTES);
+      const unsigned dst = base + st * tma::STAGE_BYTES + warp * tma::BOX_BYTES;
+      const int kin = kb + fl * BK + (warp & 1) * tma::BOXK;
+      if (warp < 2) tma::load_box(dst, &tmA, a_k + kin, a_r, bar);
+      else tma::load_box(dst, &tmB, b_k + kin, b_r, bar);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < tma::NST - 1; s++)
+    if (s < nk) issue(s);
+  double acc[T::MT][T::NT][2];
+#pragma unroll
+  for (int i = 0; i < T::MT; i++)
+#pragma unroll
+    for (int j = 0; j < T::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int f = 0; f < nk; f++) {
+    const int st = f % tma::NST;
+    tma::mbar_wait(full0 + 8 * st, (unsigned)((f / tma::NST) & 1));
+    const unsigned char* sa = sbase + st * tma::STAGE_BYTES;
+    const unsigned char* sb = sa + 2 * tma::BOX_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; kk++) {
+      const unsigned bo = (unsigned)(kk >> 2) * tma::BOX_BYTES + koff[kk & 3];
+      double a[T::MT], b[T::NT];
+#pragma unroll
+      for (int i = 0; i < T::MT; i++) a[i] = *reinterpret_cast<const double*>(sa + bo + rowA + i * 1024);
+#pragma unroll
+      for (int j = 0; j < T::NT; j++) b[j] = *reinterpret_cast<const double*>(sb + bo + rowB + j * 1024);
+#pragma unroll
+      for (int i = 0; i < T::MT; i++)
+#pragma unroll
+        for (int j = 0; j < T::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      if (kk == 0 && f + tma::NST - 1 < nk) issue(f + tma::NST - 1);
+    }
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(empty0 + 8 * st);
+  }
+  double* C = p.C + (long)node * p.c_batch_stride;
+#pragma unroll
+  for (int i = 0; i < T::MT; i++) {
+    const long r = row0 + wm0 + 8 * i + g;
+#pragma unroll
+    for (int j = 0; j < T::NT; j++) {
+      double2* ptr = reinterpret_cast<double2*>(C + r * p.ldc + col0 + wn0 + 8 * j + 2 * t);
+      double2 v;
+      v.x = p.alpha * acc[i][j][0];
+      v.y = p.alpha * acc[i][j][1];
+      if (p.beta != 0.0) {
+        double2 o = *ptr;
+        v.x += p.beta * o.x;
+        v.y += p.beta * o.y;
+      }
+      *ptr = v;
+    }
+  }
+}
+
 }  // namespace dg

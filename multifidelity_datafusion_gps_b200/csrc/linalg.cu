@@ -14,7 +14,10 @@
 #include "fastmath.cuh"
 
 #ifndef MFGP_TRMM_TMA_DEFAULT
-#define MFGP_TRMM_TMA_DEFAULT 0
+#define MFGP_TRMM_TMA_DEFAULT 1      // measured r02: 2.42 -> 2.27 ms per 75 776 x 1024 launch, bit-identical sums
+#endif
+#ifndef MFGP_GEMM_TMA_DEFAULT
+#define MFGP_GEMM_TMA_DEFAULT 0
 #endif
 
 namespace {
@@ -593,12 +596,103 @@ int tile_count(const dg::GemmParams& p) {
   return (p.lower_only ? tm * (tm + 1) / 2 : tm * tn) * (p.batch > 1 ? p.batch : 1);
 }
 
+// ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda) --------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// row-major (rows x inner) FP64 matrix, leading dimension ld: boxes of {16 doubles, 128 rows}, 128-byte swizzle
+static bool make_map(CUtensorMap* m, const double* base, unsigned long long inner, unsigned long long rows,
+                     unsigned long long ld) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {ld * sizeof(double)};
+  cuuint32_t box[2] = {dg::tma::BOXK, 128};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// MFGP_TRMM_TMA=1|0 selects the TMA + mbarrier variant of trmm_sumsq, MFGP_GEMM_TMA=1|0 that of the NT GEMMs
+// (read once)
+static int trmm_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFGP_TRMM_TMA");
+    v = e ? (atoi(e) != 0) : MFGP_TRMM_TMA_DEFAULT;
+  }
+  return v;
+}
+static int gemm_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFGP_GEMM_TMA");
+    v = e ? (atoi(e) != 0) : MFGP_GEMM_TMA_DEFAULT;
+  }
+  return v;
+}
+
+
+// NT product through the TMA kernel (k-contiguous operands, full 128 x 128 tiles on at least one wave).
+// Returns 1 if it took the launch.
+static int try_gemm_tma(mfgp_ctx* h, const dg::GemmParams& p, int cls) {
+  if (!gemm_tma_enabled()) return 0;
+  const int nodes = p.batch > 1 ? p.batch : 1;
+  // operand views: A is (M + node shifts) x K, B is (N + node shifts) x K; the leading dimension bounds k
+  const long shift = nodes > 1 ? p.batch_stride : 0;      // elements per node along the diagonal: n * (ld + 1)
+  long a_rows_shift = 0, a_k_shift = 0, b_rows_shift = 0, b_k_shift = 0, c_stride = 0;
+  if (nodes > 1) {
+    // batch_stride = n * (ld + 1) for all three operands (equal leading dimensions): n rows down, n columns right
+    if (p.lda != p.ldb || p.lda != p.ldc) return 0;
+    const long n = shift / (p.lda + 1);
+    if (n * (p.lda + 1) != shift) return 0;
+    a_rows_shift = b_rows_shift = a_k_shift = b_k_shift = n;
+    c_stride = shift;
+  }
+  CUtensorMap tmA, tmB;
+  const unsigned long long a_rows = (unsigned long long)p.M + (nodes - 1) * a_rows_shift;
+  const unsigned long long b_rows = (unsigned long long)p.N + (nodes - 1) * b_rows_shift;
+  const unsigned long long kext = (unsigned long long)p.K + (nodes - 1) * a_k_shift;
+  if (!make_map(&tmA, p.A, kext, a_rows, p.lda) || !make_map(&tmB, p.B, kext, b_rows, p.ldb)) return 0;
+  dg::GemmTmaParams q;
+  memset(&q, 0, sizeof(q));
+  q.C = p.C; q.ldc = p.ldc; q.M = p.M; q.N = p.N; q.K = p.K; q.alpha = p.alpha; q.beta = p.beta;
+  q.lower_only = p.lower_only; q.kb_row = p.kb_row; q.kb_col = p.kb_col; q.ke_row = p.ke_row;
+  q.batch = p.batch; q.c_batch_stride = c_stride;
+  q.a_batch_rows = (int)a_rows_shift; q.a_batch_k = (int)a_k_shift;
+  q.b_batch_rows = (int)b_rows_shift; q.b_batch_k = (int)b_k_shift;
+  prof_begin(h, cls);
+  dg::gemm_tma_kernel<dg::Big16><<<tile_count<dg::Big16>(p), dg::Big16::THREADS, dg::tma::SMEM_BYTES, h->stream>>>(
+      tmA, tmB, q);
+  prof_end(h, cls);
+  return 1;
+}
+
 // Narrow GEMMs (fewer 128x128 tiles than SMs) sit on the critical path of the recursion: run them
 // with 64x64 tiles so that four times as many SMs share the work.
 template <bool A_KC, bool B_KC>
 int launch_gemm(mfgp_ctx* h, const dg::GemmParams& p, int cls = PC_GEMM) {
   const int big_tiles = tile_count<dg::Big>(p);
   if (big_tiles <= 0) return 0;
+  if (A_KC && B_KC && big_tiles >= MFGP_NUM_SMS && tile_variant() == 16 && try_gemm_tma(h, p, cls)) {
+    LAUNCH_CHECK(h);
+    return 0;
+  }
   prof_begin(h, cls);
   if (big_tiles < MFGP_NUM_SMS) {
     dg::gemm_kernel<dg::Small, A_KC, B_KC>
@@ -737,6 +831,8 @@ int linalg_configure(mfgp_ctx* h) {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, dg::Big16::SMEM_BYTES));
   CUDA_TRY(h, cudaFuncSetAttribute(dg::trmm_sumsq_tma_kernel<dg::Big16>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, dg::tma::SMEM_BYTES));
+  CUDA_TRY(h, cudaFuncSetAttribute(dg::gemm_tma_kernel<dg::Big16>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::tma::SMEM_BYTES));
   rc |= configure_gemm<dg::Big16, true, true>(h);
   rc |= configure_gemm<dg::Big16, false, true>(h);
   rc |= configure_gemm<dg::Big16, false, false>(h);
@@ -756,7 +852,11 @@ static int LA_NB_ENV = 0;     // MFGP_LA_NB overrides the panel width (multiple 
 constexpr int LA_MIN = 4096;    // below this the plain recursion is as fast
 constexpr int LA_MAXP = 64;
 // measured at N = 16384: 512 -> 55.1 ms, 768 -> 55.4, 1024 -> 56.3, 2048 -> 61.2 (profiles/r01_notes.md)
-static int LA_TAIL = 4096;      // MFGP_LA_TAIL: remaining columns at which the plain recursion takes over (0: never)
+// MFGP_LA_TAIL: remaining columns at which the plain recursion would take over from the panels.  Measured at
+// N = 16384 (profiles/r02_potrf_tail.txt): 0 -> 53.8 ms, 2048 -> 53.9, 4096 -> 54.6, 6144 -> 56.0, 8192 -> 57.8:
+// the recursion loses at every size (its half-size TRSM / SYRK expose MORE serial leaf chain, not less), so the
+// switch stays off; kept for the record and for other shapes.
+static int LA_TAIL = 0;
 static int la_nb(int npad) { return LA_NB_ENV ? LA_NB_ENV : (npad <= 512 * LA_MAXP ? 512 : 1024); }
 
 static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
@@ -913,48 +1013,6 @@ int trmm_right_store(mfgp_ctx* h, const double* L, int n, const double* E, long 
   dg::GemmParams p = gp(L, n, E, ldc, Z, ldc, n, (int)ldc, n, 1.0, 0.0);
   p.ke_row = 1;
   return launch_gemm<true, false>(h, p, PC_MISC);
-}
-
-// ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda) --------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// row-major (rows x inner) FP64 matrix, leading dimension ld: boxes of {16 doubles, 128 rows}, 128-byte swizzle
-static bool make_map(CUtensorMap* m, const double* base, unsigned long long inner, unsigned long long rows,
-                     unsigned long long ld) {
-  EncodeTiledFn fn = encode_tiled();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {inner, rows};
-  cuuint64_t strides[1] = {ld * sizeof(double)};
-  cuuint32_t box[2] = {dg::tma::BOXK, 128};
-  cuuint32_t estr[2] = {1, 1};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-// MFGP_TRMM_TMA=1|0 selects the TMA + mbarrier variant of trmm_sumsq (read once)
-static int trmm_tma_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MFGP_TRMM_TMA");
-    v = e ? (atoi(e) != 0) : MFGP_TRMM_TMA_DEFAULT;
-  }
-  return v;
 }
 
 int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad,

@@ -194,7 +194,10 @@ __global__ void build_mc_rows_kernel(const double* __restrict__ Xtest, const dou
 // (exp2s units, see KParams) and every (sample, k) element then costs ONE exponential:
 //   Ks[(m,s)][k] = exp2s(uz (z_s - Z_k)^2 + su[k]) + sv[k],   mu[(m,s)] = sum_k Ks alpha_k.
 // Columns are written with 16-byte stores; the per-sample mean is reduced in a fixed order.
-constexpr int MC_KCHUNK = 1024;   // k values staged per pass (4 arrays x 8 KB, static smem)
+// Shared memory per CTA decides how many test points an SM works on at once (the kernel is bound by HBM
+// write latency, ncu r01: dram 43 %, 2 CTAs / SM): 512 staged k values (4 arrays x 4 KB) and sample arrays
+// sized by S leave room for four CTAs per SM at S = 100 (50 KB each) instead of two (80 KB).
+constexpr int MC_KCHUNK = 512;    // k values staged per pass (static smem)
 constexpr int MC_MAXS = 1024;
 
 __global__ void __launch_bounds__(256)
@@ -204,10 +207,10 @@ __global__ void __launch_bounds__(256)
                         const double* __restrict__ eps, unsigned long long seed, long long m_global0,
                         long long m_lo, int S, double* __restrict__ Ks, double* __restrict__ mu_c,
                         const double* __restrict__ zcol, long long z_off, long long ldz) {
-  extern __shared__ __align__(16) double stbl_all[];   // exp table (32 KB) | zs[MC_MAXS]
+  extern __shared__ __align__(16) double stbl_all[];   // exp table (32 KB) | zs[S rounded up] | macc[S rounded up]
   __shared__ __align__(16) double su[MC_KCHUNK], sv[MC_KCHUNK], sz[MC_KCHUNK], sa[MC_KCHUNK];
-  __shared__ double macc[MC_MAXS];
   double* zs = stbl_all + fm::EXP_TBL_DOUBLES;
+  double* macc = zs + ((S + 31) & ~31);
   fm::load_exp_table(stbl_all, kp.exp_tbl);
   const unsigned tbl = fm::lane_table(stbl_all);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -484,6 +487,100 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
   }
   if (threadIdx.x == 0) path[s] += sv[0];
+}
+
+// ---- latency path: a handful of query rows, one CTA each, results straight into mapped host memory ----------
+// The reference's default acquisition is a sequential DIRECT search of up to 20 000 single-point predicts
+// (src/adaptation_maximizers/scipydirect_wrapper.py:22-26).  Through mfgp_predict every one of them costs an
+// upload, three launches and two downloads (~130 us); here it is one or two launches and ONE synchronisation:
+// the query row is read from, and (mean, variance) written to, pinned host memory mapped into the device.
+constexpr int PS_MAXN = 2048;     // training points (kx lives in shared memory)
+
+__device__ __forceinline__ double small_kernel_value(const KParams& kp, const double* __restrict__ q,
+                                                     const double* __restrict__ xk, unsigned tbl) {
+  double rx = 0.0, rz = 0.0;
+  for (int dd = 0; dd < kp.D; dd++) {
+    const double t = q[dd] - xk[dd];
+    if (dd < kp.d) rx = fma(t, t, rx);
+    else rz = fma(t, t, rz);
+  }
+  double v = fm::exp2s_flat(fma(kp.uz, rz, fma(kp.ux, rx, kp.lc12)), tbl);
+  if (kp.s3 != 0.0) v += fm::exp2s_flat(fma(kp.u3, rx, kp.ls3), tbl);
+  return v;
+}
+
+// Xaug[m] = [x_m, mu_l(x_m + o_0 tau), ...]: one CTA per (row, location); fixed-order block reduction
+__global__ void __launch_bounds__(256)
+    augment_small_kernel(KParams kl, const double* __restrict__ Xl, int Nl, const double* __restrict__ alpha_l,
+                         const double* __restrict__ Xq, int d, const double* __restrict__ offs, int E,
+                         double tau, double* __restrict__ Xaug) {
+  __shared__ double stbl[256];
+  __shared__ double red[256];
+  __shared__ double loc[MFGP_MAX_D];
+  const int m = blockIdx.x / E, e = blockIdx.x - m * E, tid = threadIdx.x;
+  stbl[tid] = kl.exp_tbl[tid];
+  if (tid < d) loc[tid] = Xq[m * d + tid] + offs[e * d + tid] * tau;
+  __syncthreads();
+  const unsigned tbl = (unsigned)__cvta_generic_to_shared(stbl);
+  double acc = 0.0;
+  for (int k = tid; k < Nl; k += 256) acc = fma(small_kernel_value(kl, loc, Xl + (long)k * kl.D, tbl), alpha_l[k], acc);
+  red[tid] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  double* row = Xaug + (long)m * (d + E);
+  if (tid == 0) row[d + e] = red[0];
+  if (e == 0 && tid < d) row[tid] = Xq[m * d + tid];
+}
+
+// (mean, var) of one query row per CTA: kx in shared memory, mean by a fixed-order block reduction, then
+// tmp = W kx with one warp per row of W (coalesced), sum of squares in a fixed order
+__global__ void __launch_bounds__(256)
+    predict_small_kernel(KParams kp, const double* __restrict__ X, int N, int npad,
+                         const double* __restrict__ alpha, const double* __restrict__ W,
+                         const double* __restrict__ Xq, double noise_add, double* __restrict__ out /* (M, 2) */) {
+  __shared__ double stbl[256];
+  __shared__ double kx[PS_MAXN];
+  __shared__ double red[256];
+  __shared__ double wss[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* q = Xq + (long)blockIdx.x * kp.D;
+  stbl[tid] = kp.exp_tbl[tid];
+  __syncthreads();
+  const unsigned tbl = (unsigned)__cvta_generic_to_shared(stbl);
+  double acc = 0.0;
+  for (int k = tid; k < N; k += 256) {
+    const double v = small_kernel_value(kp, q, X + (long)k * kp.D, tbl);
+    kx[k] = v;
+    acc = fma(v, alpha[k], acc);
+  }
+  red[tid] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  double ss = 0.0;
+  for (int i = warp; i < N; i += 8) {
+    const double* row = W + (long)i * npad;
+    double t = 0.0;
+    for (int k = lane; k <= i; k += 32) t = fma(row[k], kx[k], t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    ss = fma(t, t, ss);
+  }
+  if (lane == 0) wss[warp] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; w++) s += wss[w];
+    double v = kp.kdiag - s;
+    v = v < 1e-15 ? 1e-15 : v;   // GPy posterior.py: np.clip(var, 1e-15, inf)
+    out[2 * blockIdx.x] = red[0];
+    out[2 * blockIdx.x + 1] = v + noise_add;
+  }
 }
 
 // ---- deterministic reductions -----------------------------------------------------------------
@@ -773,7 +870,7 @@ int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, 
   if (npts <= 0) return 0;
   ARG_CHECK(h, S <= MC_MAXS);
   prof_begin(h, PC_CROSSGEN);
-  cross_gen_mc_kernel<<<(unsigned)npts, 256, fm::EXP_TBL_BYTES + MC_MAXS * sizeof(double), h->stream>>>(
+  cross_gen_mc_kernel<<<(unsigned)npts, 256, fm::EXP_TBL_BYTES + 2 * ((S + 31) & ~31) * sizeof(double), h->stream>>>(
       kp, X, N, npad, alpha, Xtest, mu_l, sd_l, eps, seed, m_global0, m_lo, S, Ks, mu_c, zcol, z_off, ldz);
   prof_end(h, PC_CROSSGEN);
   LAUNCH_CHECK(h);
@@ -789,7 +886,7 @@ int mc_max_samples() { return MC_MAXS; }
 
 int predict_configure(mfgp_ctx* h) {
   CUDA_TRY(h, cudaFuncSetAttribute(cross_gen_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   fm::EXP_TBL_BYTES + MC_MAXS * (int)sizeof(double)));
+                                   fm::EXP_TBL_BYTES + 2 * MC_MAXS * (int)sizeof(double)));
   return 0;
 }
 
@@ -943,6 +1040,26 @@ int path_wsum_launch(mfgp_ctx* h, const double* mu_c, const double* w, long long
                      double* path) {
   if (npts <= 0 || S <= 0) return 0;
   path_wsum_kernel<<<S, 256, 0, h->stream>>>(mu_c, w, m_lo, npts, S, path);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int predict_small_max_n() { return PS_MAXN; }
+
+// lf may be null (Xq already augmented, width kp.D); else Xq holds plain inputs (width d) and Xaug_tmp
+// receives the augmented rows.  All pointers device-accessible (mapped host memory included).
+int predict_small_launch(mfgp_ctx* h, const KParams& kh, const mfgp_level_t* hf, const KParams* kl,
+                         const mfgp_level_t* lf, const double* Xq, int M, const double* d_offs, int E, double tau,
+                         double* Xaug_tmp, double noise_add, double* out) {
+  const int npad = mfgp_padded_n(hf->N);
+  const double* rows = Xq;
+  if (lf) {
+    augment_small_kernel<<<M * E, 256, 0, h->stream>>>(*kl, lf->d_X, lf->N, lf->d_alpha, Xq, lf->D, d_offs, E, tau,
+                                                       Xaug_tmp);
+    LAUNCH_CHECK(h);
+    rows = Xaug_tmp;
+  }
+  predict_small_kernel<<<M, 256, 0, h->stream>>>(kh, hf->d_X, hf->N, npad, hf->d_alpha, hf->d_W, rows, noise_add, out);
   LAUNCH_CHECK(h);
   return 0;
 }

@@ -290,16 +290,18 @@ class GPRegression:
         (evaluate it through ``lml_and_grad``, which replays the jitter schedule)."""
         assert self.N <= SMALL_BATCH_N, "the batched objective serves N <= %d" % SMALL_BATCH_N
         h = handle if handle is not None else _ffi.get_handle(self.device)
-        thetas = np.ascontiguousarray(thetas, dtype=np.float64).reshape(-1, len(self.names))
-        B, P = thetas.shape
+        P = len(self.kern.names) + 1
+        thetas = np.ascontiguousarray(thetas, dtype=np.float64).reshape(-1, P)
+        B = thetas.shape[0]
         lml = np.empty(B)
         grad = np.empty((B, P))
         info = np.zeros(B, dtype=np.int32)
-        vp = ctypes.c_void_p
-        h.check(h.lib.mfgp_lml_grad_batch(
+        rc = h.lib.mfgp_lml_grad_batch(
             h.h, self.kern.kind, self._dX.data_ptr(), self._dy.data_ptr(), self.N, self.D, self.kern.d,
-            thetas.ctypes.data_as(vp), P, B, 0.0, lml.ctypes.data_as(vp),
-            grad.ctypes.data_as(vp) if want_grad else None, info.ctypes.data_as(vp)))
+            thetas.ctypes.data, P, B, 0.0, lml.ctypes.data, grad.ctypes.data if want_grad else None,
+            info.ctypes.data)
+        if rc != 0:
+            h.check(rc)
         self.n_evals += B
         return lml, grad, info
 
@@ -517,19 +519,29 @@ class GPRegression:
         infeasible point / failed factorisation (paramz counts both as failures).  A vector whose
         factorisation met a non-positive pivot is re-evaluated through lml_and_grad, which replays GPy's
         jitter schedule."""
-        thetas = np.asarray(thetas, dtype=np.float64).reshape(-1, len(self.names))
-        ok = np.array([self._feasible(th) for th in thetas], dtype=bool)
+        thetas = np.asarray(thetas, dtype=np.float64).reshape(-1, len(self.kern.names) + 1)
+        # feasible: finite, kernel parameters > 0, noise >= 0 (see _feasible), for the whole batch at once
+        ok = np.isfinite(thetas).all(axis=1) & (thetas[:, :-1] > 0.0).all(axis=1) & (thetas[:, -1] >= 0.0)
         out = [None] * len(thetas)
-        if ok.any():
-            lml, grad, info = self.lml_and_grad_batch(thetas[ok], handle=handle)
-            for b, l, g, bad in zip(np.flatnonzero(ok), lml, grad, info):
-                if bad != 0:
+        if ok.all():
+            rows, sel = range(len(thetas)), thetas
+        else:
+            rows, sel = np.flatnonzero(ok), thetas[ok]
+        if len(sel):
+            lml, grad, info = self.lml_and_grad_batch(sel, handle=handle)
+            chain = logexp_gradfactor(sel[:, free])           # d theta / d x of the Logexp transform
+            obj_grad = -(grad[:, free] * chain)
+            fin = np.isfinite(lml) & np.isfinite(obj_grad).all(axis=1)
+            for k, b in enumerate(rows):
+                if info[k] != 0:
                     try:
-                        l, g = self.lml_and_grad(thetas[b])
+                        l, g = self.lml_and_grad(sel[k])
                     except NotPositiveDefinite:
                         continue
-                if np.isfinite(l) and np.all(np.isfinite(g)):
-                    out[b] = (-float(l), -(g[free] * logexp_gradfactor(thetas[b][free])))
+                    if np.isfinite(l) and np.all(np.isfinite(g)):
+                        out[b] = (-float(l), -(g[free] * logexp_gradfactor(sel[k][free])))
+                elif fin[k]:
+                    out[b] = (-float(lml[k]), obj_grad[k])
         return out
 
     def _optimize_lockstep(self, indices, starts, robust, max_iters=1000, **_):
@@ -546,10 +558,10 @@ class GPRegression:
         nfree = int(free.sum())
         base = self.param_array.copy()
 
-        def theta_of(x):
-            theta = base.copy()
-            theta[free] = logexp_f(x)
-            return theta
+        def thetas_of(xs):                                   # one Logexp transform for the whole round
+            thetas = np.tile(base, (len(xs), 1))
+            thetas[:, free] = logexp_f(np.array(xs))
+            return thetas
         runs = {i: _lbfgsb.LbfgsbRun(logexp_finv(base[free]) if starts[i] is None
                                      else logexp_finv(logexp_f(starts[i])), max_iters, max_iters) for i in indices}
         fails = {i: 0 for i in indices}
@@ -558,7 +570,7 @@ class GPRegression:
             want = [i for i in indices if i not in errors and runs[i].advance()]
             if not want:
                 break
-            vals = self._objective_batch([theta_of(runs[i].x) for i in want], free)
+            vals = self._objective_batch(thetas_of([runs[i].x for i in want]), free)
             for i, v in zip(want, vals):
                 if v is None:
                     if fails[i] >= 10:                     # paramz: more than ten failures in a row re-raise
@@ -574,7 +586,7 @@ class GPRegression:
             raise errors[min(errors)]
         done = [i for i in indices if i not in errors]
         # paramz opt_lbfgsb.opt: f_opt = f_fp(x_opt)[0], for all runs in one more batched launch
-        final = self._objective_batch([theta_of(runs[i].x) for i in done], free) if done else []
+        final = self._objective_batch(thetas_of([runs[i].x for i in done]), free) if done else []
         return [(i, (v[0] if v is not None else np.inf), np.array(runs[i].x, dtype=np.float64))
                 for i, v in zip(done, final)]
 

@@ -816,3 +816,30 @@ def test_mc_with_joint_lf_sampling_across_test_points(pkg):
     # a joint covariance that is not positive definite is reported, not silently sampled from
     with pytest.raises(np.linalg.LinAlgError):
         m.predict_mc(Xt[:20], n_samples=8, seed=1, joint=True, lf_jitter=-10.0)
+
+
+def test_predict_point_latency_path_matches_predict(pkg):
+    # mfgp_predict_small: what one DIRECT objective evaluation costs (scipydirect_wrapper.py:22-26)
+    lf_X, X_hf, _ = _data(2, n_hf=9)
+    rs = np.random.RandomState(3)
+    models = []
+    m = pkg.GPDF(2, 0.001, 2, util.hf_2d, util.lf_2d)                        # callable LF, delays (D = 7)
+    m.fit(X_hf, theta=THETA_R)
+    models.append(m)
+    m = pkg.NARGP(2, util.hf_2d, None, lf_X=lf_X, lf_Y=util.lf_2d(lf_X))     # data-driven LF
+    m.lf_model._set_params(np.array([1.5, 0.4, 1e-3]))
+    m.fit(X_hf, theta=THETA_C)
+    models.append(m)
+    m = pkg.GPDFC(2, 0.05, 2, util.hf_2d, None, lf_X=lf_X, lf_Y=util.lf_2d(lf_X))   # data-driven LF with delays
+    m.lf_model._set_params(np.array([1.5, 0.4, 1e-3]))
+    m.fit(np.vstack([X_hf, rs.uniform(size=(150, 2))]), theta=THETA_C)       # N_h = 159: beyond one 128-tile
+    models.append(m)
+    for m in models:
+        for M in (1, 5, 16):
+            Xq = rs.uniform(size=(M, 2))
+            mu, var = m.predict(Xq)
+            mu_p, var_p = m.predict_point(Xq)
+            assert mu_p.shape == (M, 1) and var_p.shape == (M, 1)
+            assert util.rel_err(mu_p, mu) < 1e-11 and util.rel_err(var_p, var, 1.2) < 1e-10
+        mu_f, var_f = m.predict_point(rs.uniform(size=(40, 2)))               # too many rows: falls back
+        assert mu_f.shape == (40, 1)
