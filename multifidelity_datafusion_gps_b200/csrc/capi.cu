@@ -503,6 +503,14 @@ static int level_kparams(mfgp_ctx* h, const mfgp_level_t* gp, KParams* kp) {
   return make_kparams(h, gp->kind, gp->D, gp->d, gp->h_theta, gp->P, kp);
 }
 
+// Column chunks are sized in whole waves of 128-column tiles (one CTA per SM): a chunk of 149 tiles costs two
+// waves, i.e. twice the time of 148 (found the hard way: a scratch that grew by 0.1 % doubled the
+// low-fidelity stage of the MC sweep).  Results never depend on the chunk size.
+static long long whole_waves(long long cols) {
+  const long long wave = (long long)MFGP_NUM_SMS * 128;
+  return cols > wave ? cols / wave * wave : cols;
+}
+
 static int predict_impl(mfgp_ctx* h, const mfgp_level_t* gp, const KParams& kp, const double* d_Xnew,
                         long long M, double* d_mean, double* d_var, int include_noise, double* d_ws,
                         size_t ws_bytes) {
@@ -515,7 +523,7 @@ static int predict_impl(mfgp_ctx* h, const mfgp_level_t* gp, const KParams& kp, 
   }
   ARG_CHECK(h, gp->d_W != nullptr && d_ws != nullptr);
   const long long per_col = (long long)npad + 1;
-  long long chunk = (long long)(ws_bytes / sizeof(double)) / per_col / 128 * 128;
+  long long chunk = whole_waves((long long)(ws_bytes / sizeof(double)) / per_col / 128 * 128);
   ARG_CHECK(h, chunk >= 128);
   double* Ks = d_ws;
   double* ss = d_ws + chunk * npad;
@@ -661,7 +669,7 @@ static int mc_chain_impl(mfgp_ctx* h, const mfgp_level_t* const* levels, int L, 
   // upper levels over (point, sample) columns
   const int D = d + 1;
   const long long per_col = (long long)npad_max + D + 3;
-  long long max_cols = restd / per_col / 128 * 128;
+  long long max_cols = whole_waves(restd / per_col / 128 * 128);
   ARG_CHECK(h, max_cols >= 128);
   long long pm = max_cols / S;
   ARG_CHECK(h, pm >= 1);   // the scratch must hold all S samples of at least one point
@@ -803,7 +811,7 @@ int mfgp_predict_mc_joint(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_le
   if (d_path_wsum) CUDA_TRY(h, cudaMemsetAsync(d_path_wsum, 0, (size_t)S * sizeof(double), h->stream));
   // high-fidelity level over (point, sample) columns
   const long long per_col = (long long)nph + 3;
-  long long max_cols = restd / per_col / 128 * 128;
+  long long max_cols = whole_waves(restd / per_col / 128 * 128);
   ARG_CHECK(h, max_cols >= 128);
   long long pm = max_cols / S;
   ARG_CHECK(h, pm >= 1);

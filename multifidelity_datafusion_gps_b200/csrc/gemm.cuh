@@ -710,4 +710,165 @@ __global__ void __launch_bounds__(T::THREADS, 1)
   }
 }
 
+// ---- TMA GEMM with an m-contiguous operand (TN / TT products: triangular inverse, K^-1 = W^T W) -------------
+// An operand stored as X(m,k) = X[k*ld + m] is fetched as eight boxes of {16 m values (128 B), 32 k rows};
+// box b holds m = 16 b .. 16 b + 15.  With the 128-byte swizzle, a DMMA step that took the four CONSECUTIVE k
+// rows 4 kk .. 4 kk + 3 would put the four t-groups of a warp on the same 64 bytes of banks (4 wavefronts per
+// LDS instead of 2), because consecutive rows only permute the low chunk bits.  A step therefore takes the k
+// rows {b, b+1, b+4, b+5} with b = 8 (kk / 2) + 2 (kk % 2): rows b+4, b+5 flip chunk bit 2, the 32 lanes
+// cover all 32 banks twice -- the minimum for 256 bytes.  Any grouping of the 32 k values of a slab into eight
+// steps is a valid DMMA schedule as long as both operands use the same one; a k-contiguous partner operand
+// reads the same k sets from its {16 k, 128 rows} boxes (also 2 wavefronts).  The accumulation order over k
+// differs from gemm_kernel's, so results agree with it to round-off, not bit for bit.
+template <class T, bool A_KC, bool B_KC>
+__global__ void __launch_bounds__(T::THREADS, 1)
+    gemm_tma_mc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       GemmTmaParams p) {
+  static_assert(T::BM == 128 && T::BN == 128 && BK == 32 && T::THREADS == 512, "16 warps, 128 x 128 x 32 slabs");
+  static_assert(!(A_KC && B_KC), "k-contiguous pairs take gemm_tma_kernel");
+  constexpr int A_BOXES = A_KC ? 2 : 8, B_BOXES = B_KC ? 2 : 8;
+  constexpr int A_BOX_BYTES = A_KC ? tma::BOX_BYTES : 4096, B_BOX_BYTES = B_KC ? tma::BOX_BYTES : 4096;
+  constexpr int OPND_BYTES = 2 * tma::BOX_BYTES;          // 32 KB per operand and stage, either layout
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * tma::NST];
+  const unsigned raw = tma::smem_u32(smem_raw);
+  const unsigned base = (raw + 1023u) & ~1023u;
+  const unsigned char* sbase = smem_raw + (base - raw);
+  const unsigned full0 = tma::smem_u32(&bars[0]), empty0 = tma::smem_u32(&bars[tma::NST]);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp / T::WGN) * T::WTM, wn0 = (warp % T::WGN) * T::WTN;
+  int ti, tj, node = 0;
+  int bid = blockIdx.x;
+  if (p.batch > 1) {
+    const int per_node = gridDim.x / p.batch;
+    node = bid / per_node;
+    bid %= per_node;
+  }
+  if (p.lower_only) {
+    int tt = bid;
+    ti = (int)((sqrt(8.0 * tt + 1.0) - 1.0) * 0.5);
+    while ((long)(ti + 1) * (ti + 2) / 2 <= tt) ti++;
+    while ((long)ti * (ti + 1) / 2 > tt) ti--;
+    tj = tt - ti * (ti + 1) / 2;
+  } else {
+    const int tiles_n = p.N / T::BN;
+    ti = bid / tiles_n;
+    tj = bid % tiles_n;
+  }
+  const int row0 = ti * T::BM, col0 = tj * T::BN;
+  int kb = 0, ke = p.K;
+  if (p.kb_row) kb = max(kb, row0);
+  if (p.kb_col) kb = max(kb, col0);
+  if (p.ke_row) ke = min(ke, row0 + T::BM);
+  const int nk = ke > kb ? (ke - kb) / BK : 0;
+  if (tid == 0) {
+    for (int s = 0; s < tma::NST; s++) {
+      tma::mbar_init(full0 + 8 * s, A_BOXES + B_BOXES);
+      tma::mbar_init(empty0 + 8 * s, T::THREADS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  // k rows of step kk: k = 8 (kk >> 1) + 2 (kk & 1) + (t & 1) + 4 (t >> 1)
+  const int kt = (t & 1) + 4 * (t >> 1);
+  // k-contiguous operand: box kk >> 2, row r, chunk ((k & 15) >> 1) ^ (r & 7), half k & 1 = t & 1
+  //   (k & 15) >> 1 = 4 ((kk >> 1) & 1) + (kk & 1) + 2 (t >> 1)
+  unsigned kcoff[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    kcoff[q] = ((((unsigned)(4 * (q >> 1) + (q & 1) + 2 * (t >> 1))) ^ (unsigned)g) << 4) + (unsigned)(t & 1) * 8u;
+  // m-contiguous operand: box (m >> 4), row k, chunk ((m & 15) >> 1) ^ (k & 7), half m & 1 = g & 1, with
+  //   m & 15 = 8 (i & 1) + g  and  k & 7 = 2 (kk & 1) + kt
+  unsigned mcoff[2][2];
+#pragma unroll
+  for (int io = 0; io < 2; io++)
+#pragma unroll
+    for (int ko = 0; ko < 2; ko++)
+      mcoff[io][ko] = ((((unsigned)(4 * io + (g >> 1))) ^ (unsigned)(2 * ko + kt)) << 4) + (unsigned)(g & 1) * 8u +
+                      (unsigned)kt * 128u;
+  const int a_r = row0 + node * p.a_batch_rows, a_k = node * p.a_batch_k;
+  const int b_r = col0 + node * p.b_batch_rows, b_k = node * p.b_batch_k;
+  auto issue = [&](int fl) {
+    if (lane == 0 && warp < A_BOXES + B_BOXES) {
+      const int st = fl % tma::NST;
+      if (fl >= tma::NST) tma::mbar_wait(empty0 + 8 * st, (unsigned)((fl / tma::NST - 1) & 1));
+      const unsigned bar = full0 + 8 * st;
+      const int k0 = kb + fl * BK;
+      const unsigned sbase_st = base + st * tma::STAGE_BYTES;
+      if (warp < A_BOXES) {
+        tma::mbar_expect_tx(bar, A_BOX_BYTES);
+        if (A_KC) tma::load_box(sbase_st + warp * A_BOX_BYTES, &tmA, a_k + k0 + warp * tma::BOXK, a_r, bar);
+        else tma::load_box(sbase_st + warp * A_BOX_BYTES, &tmA, a_r + warp * 16, a_k + k0, bar);
+      } else {
+        const int w = warp - A_BOXES;
+        tma::mbar_expect_tx(bar, B_BOX_BYTES);
+        if (B_KC) tma::load_box(sbase_st + OPND_BYTES + w * B_BOX_BYTES, &tmB, b_k + k0 + w * tma::BOXK, b_r, bar);
+        else tma::load_box(sbase_st + OPND_BYTES + w * B_BOX_BYTES, &tmB, b_r + w * 16, b_k + k0, bar);
+      }
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < tma::NST - 1; s++)
+    if (s < nk) issue(s);
+  double acc[T::MT][T::NT][2];
+#pragma unroll
+  for (int i = 0; i < T::MT; i++)
+#pragma unroll
+    for (int j = 0; j < T::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  // fixed parts of the fragment addresses
+  const unsigned a_fix = A_KC ? (unsigned)(wm0 + g) * 128u : (unsigned)(wm0 >> 4) * 4096u;
+  const unsigned b_fix = B_KC ? (unsigned)(wn0 + g) * 128u : (unsigned)(wn0 >> 4) * 4096u;
+  for (int f = 0; f < nk; f++) {
+    const int st = f % tma::NST;
+    tma::mbar_wait(full0 + 8 * st, (unsigned)((f / tma::NST) & 1));
+    const unsigned char* sa = sbase + st * tma::STAGE_BYTES;
+    const unsigned char* sb = sa + OPND_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; kk++) {
+      double a[T::MT], b[T::NT];
+#pragma unroll
+      for (int i = 0; i < T::MT; i++) {
+        const unsigned off = A_KC ? (unsigned)(kk >> 2) * tma::BOX_BYTES + kcoff[kk & 3] + a_fix + i * 1024u
+                                  : a_fix + (unsigned)(i >> 1) * 4096u +
+                                        (unsigned)(8 * (kk >> 1) + 2 * (kk & 1)) * 128u + mcoff[i & 1][kk & 1];
+        a[i] = *reinterpret_cast<const double*>(sa + off);
+      }
+#pragma unroll
+      for (int j = 0; j < T::NT; j++) {
+        const unsigned off = B_KC ? (unsigned)(kk >> 2) * tma::BOX_BYTES + kcoff[kk & 3] + b_fix + j * 1024u
+                                  : b_fix + (unsigned)(j >> 1) * 4096u +
+                                        (unsigned)(8 * (kk >> 1) + 2 * (kk & 1)) * 128u + mcoff[j & 1][kk & 1];
+        b[j] = *reinterpret_cast<const double*>(sb + off);
+      }
+#pragma unroll
+      for (int i = 0; i < T::MT; i++)
+#pragma unroll
+        for (int j = 0; j < T::NT; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      if (kk == 0 && f + tma::NST - 1 < nk) issue(f + tma::NST - 1);
+    }
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(empty0 + 8 * st);
+  }
+  double* C = p.C + (long)node * p.c_batch_stride;
+#pragma unroll
+  for (int i = 0; i < T::MT; i++) {
+    const long r = row0 + wm0 + 8 * i + g;
+#pragma unroll
+    for (int j = 0; j < T::NT; j++) {
+      double2* ptr = reinterpret_cast<double2*>(C + r * p.ldc + col0 + wn0 + 8 * j + 2 * t);
+      double2 v;
+      v.x = p.alpha * acc[i][j][0];
+      v.y = p.alpha * acc[i][j][1];
+      if (p.beta != 0.0) {
+        double2 o = *ptr;
+        v.x += p.beta * o.x;
+        v.y += p.beta * o.y;
+      }
+      *ptr = v;
+    }
+  }
+}
+
 }  // namespace dg

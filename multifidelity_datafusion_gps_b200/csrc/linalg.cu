@@ -17,7 +17,7 @@
 #define MFGP_TRMM_TMA_DEFAULT 1      // measured r02: 2.42 -> 2.27 ms per 75 776 x 1024 launch, bit-identical sums
 #endif
 #ifndef MFGP_GEMM_TMA_DEFAULT
-#define MFGP_GEMM_TMA_DEFAULT 0
+#define MFGP_GEMM_TMA_DEFAULT 1      // measured r02 at N = 16384: potrf 53.8 -> 51.6 ms, trtri 44.7 -> 43.6, same bits
 #endif
 
 namespace {

@@ -529,7 +529,8 @@ class GPRegression:
             rows, sel = np.flatnonzero(ok), thetas[ok]
         if len(sel):
             lml, grad, info = self.lml_and_grad_batch(sel, handle=handle)
-            chain = logexp_gradfactor(sel[:, free])           # d theta / d x of the Logexp transform
+            # d theta / d x of the Logexp transform, per vector (same reason as in thetas_of)
+            chain = np.array([logexp_gradfactor(th[free]) for th in sel])
             obj_grad = -(grad[:, free] * chain)
             fin = np.isfinite(lml) & np.isfinite(obj_grad).all(axis=1)
             for k, b in enumerate(rows):
@@ -558,9 +559,13 @@ class GPRegression:
         nfree = int(free.sum())
         base = self.param_array.copy()
 
-        def thetas_of(xs):                                   # one Logexp transform for the whole round
+        def thetas_of(xs):
+            # one Logexp transform PER run, on a vector of the length the serial loop transforms: NumPy's
+            # SIMD exp may round the same input differently in the vector body and in the loop tail, so a
+            # (runs x parameters) batch would not reproduce the serial loop bit for bit on every CPU
             thetas = np.tile(base, (len(xs), 1))
-            thetas[:, free] = logexp_f(np.array(xs))
+            for r, x in enumerate(xs):
+                thetas[r, free] = logexp_f(x)
             return thetas
         runs = {i: _lbfgsb.LbfgsbRun(logexp_finv(base[free]) if starts[i] is None
                                      else logexp_finv(logexp_f(starts[i])), max_iters, max_iters) for i in indices}
