@@ -592,6 +592,10 @@ struct GemmTmaParams {
   int batch;
   long c_batch_stride;     // elements between the C blocks of consecutive nodes
   int a_batch_rows, a_batch_k, b_batch_rows, b_batch_k;   // coordinate shifts per node
+  // C -= A B^T (alpha = -1, beta = 1) with the accumulators STARTED at -C: the tile of C is fetched while the
+  // first slabs are still in flight, and the epilogue is a plain store (no read-modify-write latency at the
+  // end of every tile, where nothing is left to hide it).  Rounds like LAPACK's in-place update.
+  int neg_init;
 };
 
 template <class T>
@@ -664,10 +668,24 @@ __global__ void __launch_bounds__(T::THREADS, 1)
   for (int s = 0; s < tma::NST - 1; s++)
     if (s < nk) issue(s);
   double acc[T::MT][T::NT][2];
+  double* C = p.C + (long)node * p.c_batch_stride;
+  if (p.neg_init) {
 #pragma unroll
-  for (int i = 0; i < T::MT; i++)
+    for (int i = 0; i < T::MT; i++) {
+      const long r = row0 + wm0 + 8 * i + g;
 #pragma unroll
-    for (int j = 0; j < T::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < T::NT; j++) {
+        const double2 o = *reinterpret_cast<const double2*>(C + r * p.ldc + col0 + wn0 + 8 * j + 2 * t);
+        acc[i][j][0] = -o.x;
+        acc[i][j][1] = -o.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < T::MT; i++)
+#pragma unroll
+      for (int j = 0; j < T::NT; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  }
   for (int f = 0; f < nk; f++) {
     const int st = f % tma::NST;
     tma::mbar_wait(full0 + 8 * st, (unsigned)((f / tma::NST) & 1));
@@ -690,7 +708,6 @@ __global__ void __launch_bounds__(T::THREADS, 1)
     __syncwarp();
     if (lane == 0) tma::mbar_arrive(empty0 + 8 * st);
   }
-  double* C = p.C + (long)node * p.c_batch_stride;
 #pragma unroll
   for (int i = 0; i < T::MT; i++) {
     const long r = row0 + wm0 + 8 * i + g;
@@ -700,7 +717,10 @@ __global__ void __launch_bounds__(T::THREADS, 1)
       double2 v;
       v.x = p.alpha * acc[i][j][0];
       v.y = p.alpha * acc[i][j][1];
-      if (p.beta != 0.0) {
+      if (p.neg_init) {
+        v.x = -acc[i][j][0];
+        v.y = -acc[i][j][1];
+      } else if (p.beta != 0.0) {
         double2 o = *ptr;
         v.x += p.beta * o.x;
         v.y += p.beta * o.y;

@@ -638,6 +638,14 @@ static int trmm_tma_enabled() {
   }
   return v;
 }
+static int gemm_neg_init() {     // MFGP_GEMM_NEG_INIT=0: read-modify-write epilogue for C -= A B^T
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFGP_GEMM_NEG_INIT");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v;
+}
 static int gemm_tma_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -676,6 +684,7 @@ static int try_gemm_tma(mfgp_ctx* h, const dg::GemmParams& p, int cls) {
   q.batch = p.batch; q.c_batch_stride = c_stride;
   q.a_batch_rows = (int)a_rows_shift; q.a_batch_k = (int)a_k_shift;
   q.b_batch_rows = (int)b_rows_shift; q.b_batch_k = (int)b_k_shift;
+  q.neg_init = gemm_neg_init() && p.alpha == -1.0 && p.beta == 1.0;
   prof_begin(h, cls);
   dg::gemm_tma_kernel<dg::Big16><<<tile_count<dg::Big16>(p), dg::Big16::THREADS, dg::tma::SMEM_BYTES, h->stream>>>(
       tmA, tmB, q);
@@ -859,6 +868,31 @@ constexpr int LA_MAXP = 64;
 static int LA_TAIL = 0;
 static int la_nb(int npad) { return LA_NB_ENV ? LA_NB_ENV : (npad <= 512 * LA_MAXP ? 512 : 1024); }
 
+// The panel's critical path, 128 columns at a time (left-looking inside the panel): leaf -> ONE in-place
+// multiply of ALL rows below by the leaf inverse -> ONE update of the next 128-column block by the panel
+// columns factorised so far.  12 launches per 512-column panel against 20 for potrf_rec + trsm_rec (whose
+// recursion buys nothing here: every one of its GEMMs is narrower than the machine, so each costs a launch
+// latency whatever its size), i.e. a shorter serial chain wherever the bulk update no longer hides it.
+// MFGP_LA_CHAIN=0 restores the recursive panel.
+static int LA_CHAIN = 1;
+static int panel_chain(mfgp_ctx* h, double* A, double* W, long ld, int c0, int w, int npad, int nreal) {
+  int rc = 0;
+  for (int j = 0; j < w && rc == 0; j += LEAF) {
+    const int cj = c0 + j;
+    if ((rc = potrf_rec(h, A, W, ld, cj, LEAF, nreal))) break;
+    const int r0 = cj + LEAF, mr = npad - r0;
+    if (mr <= 0) break;
+    double* X = A + (long)r0 * ld + cj;
+    if ((rc = launch_trsm_leaf(h, gp(X, ld, W + (long)cj * ld + cj, ld, X, ld, mr, LEAF, LEAF, 1.0, 0.0)))) break;
+    if (j + LEAF < w) {
+      // A[r0:, r0:r0+128] -= A[r0:, c0:r0] * A[r0:r0+128, c0:r0]^T   (K = j + 128)
+      const double* P = A + (long)r0 * ld + c0;
+      rc = launch_gemm<true, true>(h, gp(P, ld, P, ld, A + (long)r0 * ld + r0, ld, mr, LEAF, j + LEAF, -1.0, 1.0));
+    }
+  }
+  return rc;
+}
+
 static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
   const long ld = npad;
   cudaStream_t s_main = h->stream, s_hi = h->s_hi;
@@ -888,8 +922,12 @@ static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad, int nrea
     const int w = (npad - c0 < LA_NB) ? npad - c0 : LA_NB;
     const int m = npad - c0 - w;
     h->stream = s_hi;
-    rc = potrf_rec(h, A, W, ld, c0, w, nreal);
-    if (rc == 0 && m > 0) rc = trsm_rec(h, A, W, ld, c0 + w, m, c0, w);
+    if (LA_CHAIN) {
+      rc = panel_chain(h, A, W, ld, c0, w, npad, nreal);
+    } else {
+      rc = potrf_rec(h, A, W, ld, c0, w, nreal);
+      if (rc == 0 && m > 0) rc = trsm_rec(h, A, W, ld, c0 + w, m, c0, w);
+    }
     if (rc) break;
     if (m > 0) {
       CUDA_TRY(h, cudaEventRecord(ev_trsm[p], s_hi));
@@ -930,6 +968,8 @@ int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
     use_la = (e && atoi(e) == 0) ? 0 : 1;
     const char* tl = getenv("MFGP_LA_TAIL");
     if (tl && atoi(tl) >= 0) LA_TAIL = atoi(tl);
+    const char* ch = getenv("MFGP_LA_CHAIN");
+    if (ch) LA_CHAIN = atoi(ch) != 0;
     const char* nb = getenv("MFGP_LA_NB");
     if (nb && atoi(nb) >= 128 && atoi(nb) % 128 == 0) LA_NB_ENV = atoi(nb);
   }
