@@ -204,12 +204,13 @@ int mfgp_create(int device, mfgp_handle_t* out) {
             cudaHostGetDevicePointer((void**)&h->d_batch, h->h_batch, 0) == cudaSuccess &&
             cudaHostGetDevicePointer((void**)&h->d_batch_info, h->h_batch_info, 0) == cudaSuccess;
   for (int i = 0; ok && i < 8; i++) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
-  for (int i = 0; ok && i < 3 * 64 + 2; i++)
+  for (int i = 0; ok && i < 3 * 64 + 4; i++)
     ok = cudaEventCreateWithFlags(&h->ev_la[i], cudaEventDisableTiming) == cudaSuccess;
   if (ok) {
     int pr_least = 0, pr_greatest = 0;
     ok = cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest) == cudaSuccess &&
-         cudaStreamCreateWithPriority(&h->s_hi, cudaStreamNonBlocking, pr_greatest) == cudaSuccess;
+         cudaStreamCreateWithPriority(&h->s_hi, cudaStreamNonBlocking, pr_greatest) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&h->s_mid, cudaStreamNonBlocking, (pr_least + pr_greatest) / 2) == cudaSuccess;
   }
   if (ok) ok = cudaMemset(h->d_info, 0, 4 * sizeof(int)) == cudaSuccess;
   if (ok) {   // 2^(j/256) rounded from 64-bit-mantissa long double
@@ -238,8 +239,9 @@ int mfgp_destroy(mfgp_handle_t h) {
   cudaFreeHost(h->h_batch);
   cudaFreeHost(h->h_batch_info);
   for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
-  for (int i = 0; i < 3 * 64 + 2; i++) cudaEventDestroy(h->ev_la[i]);
+  for (int i = 0; i < 3 * 64 + 4; i++) cudaEventDestroy(h->ev_la[i]);
   if (h->s_hi) cudaStreamDestroy(h->s_hi);
+  if (h->s_mid) cudaStreamDestroy(h->s_mid);
   if (h->prof_ev) {
     for (int i = 0; i < MFGP_PROF_CLASSES * MFGP_PROF_POOL * 2; i++) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;
@@ -313,9 +315,8 @@ static int factor_enqueue(mfgp_ctx* h, const KParams& kp, const double* d_X, con
                             MFGP_UPLO_LOWER, npad)))
     return rc;
   if (ev) CUDA_TRY(h, cudaEventRecord(ev[1], h->stream));
-  if ((rc = potrf_padded(h, d_A, d_W, npad, N))) return rc;
-  if (ev) CUDA_TRY(h, cudaEventRecord(ev[2], h->stream));
-  if ((rc = trtri_padded(h, d_A, d_W, npad))) return rc;
+  // (ev[2] sits where the factorisation is complete; part of the inverse may already have run by then)
+  if ((rc = potrf_trtri_padded(h, d_A, d_W, npad, N, ev ? ev[2] : nullptr))) return rc;
   if (ev) CUDA_TRY(h, cudaEventRecord(ev[3], h->stream));
   if ((rc = solve_alpha_launch(h, d_A, d_W, npad, N, d_y, h->d_partials, d_alpha, h->d_scalars)))
     return rc;

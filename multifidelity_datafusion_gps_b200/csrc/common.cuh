@@ -50,7 +50,9 @@ struct mfgp_ctx {
   // look-ahead Cholesky: a high-priority side stream for the panel (critical-path) kernels and
   // per-panel events ordering it against the caller's stream
   cudaStream_t s_hi;
-  cudaEvent_t ev_la[3 * 64 + 2];
+  cudaStream_t s_mid;                   // medium priority: the bulk updates when the caller's stream carries the
+                                        // overlapped triangular inverse (potrf_trtri_padded)
+  cudaEvent_t ev_la[3 * 64 + 4];
   // optional per-kernel-class timing (mfgp_profile_enable): event pairs around launches
   int prof_on;
   cudaEvent_t* prof_ev;                 // [MFGP_PROF_CLASSES][MFGP_PROF_POOL][2]
@@ -111,6 +113,9 @@ int make_kparams(mfgp_ctx* h, int kind, int D, int d, const double* theta, int P
 int linalg_configure(mfgp_ctx* h);
 int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal);   // nreal <= npad: rest is identity pad
 int trtri_padded(mfgp_ctx* h, const double* L, double* W, int npad);
+// potrf_padded followed by trtri_padded, with the inverse of the LEADING half started while the factorisation's
+// serial tail leaves SMs idle; ev_mid (optional) is recorded where the factorisation is complete
+int potrf_trtri_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal, cudaEvent_t ev_mid);
 int lauum_padded(mfgp_ctx* h, const double* W, double* Kinv, int npad);
 // tmp = W[:, :]*Ks^T with fused column sum of squares:  out_ss[c] = sum_i (sum_k W[i][k] Ks[c][k])^2
 int trmm_sumsq(mfgp_ctx* h, const double* W, int npad, const double* Ks, long long cols_pad,

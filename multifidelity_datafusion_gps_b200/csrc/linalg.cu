@@ -893,17 +893,23 @@ static int panel_chain(mfgp_ctx* h, double* A, double* W, long ld, int c0, int w
   return rc;
 }
 
-static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
+// s_bulk: stream of the bulk updates (the caller's, or s_mid when the caller's stream is to carry other work
+// meanwhile -- then `join` is false and the caller of this function orders its stream after ev_la[3*LA_MAXP+1]
+// (chain) and ev_la[3*LA_MAXP+2] (bulk) itself).
+static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad, int nreal, cudaStream_t s_bulk = nullptr,
+                           bool join = true) {
   const long ld = npad;
-  cudaStream_t s_main = h->stream, s_hi = h->s_hi;
+  cudaStream_t s_caller = h->stream, s_hi = h->s_hi;
+  cudaStream_t s_main = s_bulk ? s_bulk : s_caller;
   cudaEvent_t* ev_trsm = h->ev_la;
   cudaEvent_t* ev_bulk = h->ev_la + LA_MAXP;
   cudaEvent_t ev_start = h->ev_la[3 * LA_MAXP], ev_end = h->ev_la[3 * LA_MAXP + 1];
   const int LA_NB = la_nb(npad);
   int rc = 0;
   bool bulk_pending = false;
-  CUDA_TRY(h, cudaEventRecord(ev_start, s_main));
+  CUDA_TRY(h, cudaEventRecord(ev_start, s_caller));
   CUDA_TRY(h, cudaStreamWaitEvent(s_hi, ev_start, 0));
+  if (s_main != s_caller) CUDA_TRY(h, cudaStreamWaitEvent(s_main, ev_start, 0));
   const int P = (npad + LA_NB - 1) / LA_NB;
   for (int p = 0; p < P && rc == 0; p++) {
     const int c0 = p * LA_NB;
@@ -953,27 +959,34 @@ static int potrf_lookahead(mfgp_ctx* h, double* A, double* W, int npad, int nrea
       }
     }
   }
-  h->stream = s_main;
+  h->stream = s_caller;
   cudaEventRecord(ev_end, s_hi);
-  cudaStreamWaitEvent(s_main, ev_end, 0);
+  if (s_main != s_caller) cudaEventRecord(h->ev_la[3 * LA_MAXP + 2], s_main);
+  if (join || rc) {
+    cudaStreamWaitEvent(s_caller, ev_end, 0);
+    if (s_main != s_caller) cudaStreamWaitEvent(s_caller, h->ev_la[3 * LA_MAXP + 2], 0);
+  }
   return rc;
+}
+
+static int USE_LA = -1;
+static void potrf_env() {     // tuning switches, read once
+  if (USE_LA >= 0) return;
+  const char* e = getenv("MFGP_LOOKAHEAD");
+  USE_LA = (e && atoi(e) == 0) ? 0 : 1;
+  const char* tl = getenv("MFGP_LA_TAIL");
+  if (tl && atoi(tl) >= 0) LA_TAIL = atoi(tl);
+  const char* ch = getenv("MFGP_LA_CHAIN");
+  if (ch) LA_CHAIN = atoi(ch) != 0;
+  const char* nb = getenv("MFGP_LA_NB");
+  if (nb && atoi(nb) >= 128 && atoi(nb) % 128 == 0) LA_NB_ENV = atoi(nb);
 }
 
 int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
   ARG_CHECK(h, npad > 0 && npad % LEAF == 0);
   CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
-  static int use_la = -1;
-  if (use_la < 0) {
-    const char* e = getenv("MFGP_LOOKAHEAD");
-    use_la = (e && atoi(e) == 0) ? 0 : 1;
-    const char* tl = getenv("MFGP_LA_TAIL");
-    if (tl && atoi(tl) >= 0) LA_TAIL = atoi(tl);
-    const char* ch = getenv("MFGP_LA_CHAIN");
-    if (ch) LA_CHAIN = atoi(ch) != 0;
-    const char* nb = getenv("MFGP_LA_NB");
-    if (nb && atoi(nb) >= 128 && atoi(nb) % 128 == 0) LA_NB_ENV = atoi(nb);
-  }
-  if (use_la && h->s_hi && npad >= LA_MIN && npad <= la_nb(npad) * LA_MAXP) {
+  potrf_env();
+  if (USE_LA && h->s_hi && npad >= LA_MIN && npad <= la_nb(npad) * LA_MAXP) {
     cudaStream_t caller = h->stream;
     const int rc = potrf_lookahead(h, A, W, npad, nreal);
     h->stream = caller;   // also on the error paths inside
@@ -986,17 +999,19 @@ int potrf_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal) {
 // equally shaped, so each level is TWO launches over all of its nodes (14 launches at N = 16384
 // instead of 254); the deep levels, whose single nodes fill only a fraction of the SMs, then run as
 // one grid.
-static int trtri_levels(mfgp_ctx* h, const double* L, double* W, int npad) {
+// Levels n_first .. nsub of the nodes inside the diagonal block [off, off + nsub) (ld = npad).
+static int trtri_levels_range(mfgp_ctx* h, const double* L, double* W, int npad, int off, int nsub, int n_first) {
   const long ld = npad;
+  const long o = (long)off * (ld + 1);
   int rc;
-  for (int n = 2 * LEAF; n <= npad; n *= 2) {
-    const int n1 = n / 2, nodes = npad / n;
+  for (int n = n_first; n <= nsub; n *= 2) {
+    const int n1 = n / 2, nodes = nsub / n;
     const long stride = (long)n * (ld + 1);
-    const double* W11 = W;
-    const double* W22 = W + (long)n1 * ld + n1;
-    const double* L21 = L + (long)n1 * ld;
-    double* Tt = W + n1;                  // n1 x n1 scratch in W's (unused) upper block
-    double* W21 = W + (long)n1 * ld;
+    const double* W11 = W + o;
+    const double* W22 = W + o + (long)n1 * ld + n1;
+    const double* L21 = L + o + (long)n1 * ld;
+    double* Tt = W + o + n1;              // n1 x n1 scratch in W's (unused) upper block
+    double* W21 = W + o + (long)n1 * ld;
     {  // Tt[c][r] = sum_{k>=c} W11[k][c] * L21[r][k]
       dg::GemmParams p = gp(W11, ld, L21, ld, Tt, ld, n1, n1, n1, 1.0, 0.0);
       p.kb_row = 1;
@@ -1015,11 +1030,56 @@ static int trtri_levels(mfgp_ctx* h, const double* L, double* W, int npad) {
   return 0;
 }
 
+static int trtri_levels(mfgp_ctx* h, const double* L, double* W, int npad) {
+  return trtri_levels_range(h, L, W, npad, 0, npad, 2 * LEAF);
+}
+
 int trtri_padded(mfgp_ctx* h, const double* L, double* W, int npad) {
   ARG_CHECK(h, npad > 0 && npad % LEAF == 0);
   const int m = npad / LEAF;
   if ((m & (m - 1)) == 0) return trtri_levels(h, L, W, npad);
   return trtri_rec(h, L, W, npad, 0, npad);
+}
+
+// Factorise and invert with the inverse of the leading half overlapped with the factorisation's tail.  The last
+// ~6000 columns of the look-ahead Cholesky are bound by the serial panel chain (profiles/r02_potrf_experiments.txt):
+// the trailing updates no longer fill the machine.  The triangular inverse of the LEADING half only needs
+// L[0:n/2, 0:n/2], final once the panel ending at n/2 has been solved, so its GEMMs (1/8 of the inverse's flops
+// at n = 16384) go to the caller's stream -- lowest priority -- right behind that panel's event, while the bulk
+// updates move to a medium-priority stream and the chain keeps the high-priority one.  Results are bit-identical
+// to potrf_padded + trtri_padded (same kernels on the same data; only the schedule differs).
+// MFGP_OVERLAP_TRTRI=0 switches the overlap off.
+int potrf_trtri_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal, cudaEvent_t ev_mid) {
+  static int overlap = -1;
+  if (overlap < 0) {
+    const char* e = getenv("MFGP_OVERLAP_TRTRI");
+    overlap = e ? (atoi(e) != 0) : 1;
+  }
+  const int m = npad / LEAF;
+  int rc;
+  potrf_env();
+  const bool la = USE_LA && h->s_hi && npad >= LA_MIN && npad <= la_nb(npad) * LA_MAXP && LA_TAIL == 0;
+  const int half = npad / 2;
+  if (!(overlap && la && h->s_mid && (m & (m - 1)) == 0 && npad >= 8192 && half % la_nb(npad) == 0)) {
+    if ((rc = potrf_padded(h, A, W, npad, nreal))) return rc;
+    if (ev_mid) CUDA_TRY(h, cudaEventRecord(ev_mid, h->stream));
+    return trtri_padded(h, A, W, npad);
+  }
+  ARG_CHECK(h, npad > 0 && npad % LEAF == 0);
+  CUDA_TRY(h, cudaMemsetAsync(h->d_info, 0, 4 * sizeof(int), h->stream));
+  cudaStream_t caller = h->stream;
+  rc = potrf_lookahead(h, A, W, npad, nreal, h->s_mid, false);
+  h->stream = caller;
+  if (rc) return rc;
+  // leading half: its last panel is panel half / NB - 1, whose chain (and row solves) end at ev_trsm of that panel
+  const int p_half = half / la_nb(npad) - 1;
+  CUDA_TRY(h, cudaStreamWaitEvent(caller, h->ev_la[p_half], 0));
+  if ((rc = trtri_levels_range(h, A, W, npad, 0, half, 2 * LEAF))) return rc;
+  CUDA_TRY(h, cudaStreamWaitEvent(caller, h->ev_la[3 * LA_MAXP + 1], 0));
+  CUDA_TRY(h, cudaStreamWaitEvent(caller, h->ev_la[3 * LA_MAXP + 2], 0));
+  if (ev_mid) CUDA_TRY(h, cudaEventRecord(ev_mid, caller));
+  if ((rc = trtri_levels_range(h, A, W, npad, half, half, 2 * LEAF))) return rc;
+  return trtri_levels_range(h, A, W, npad, 0, npad, npad);
 }
 
 int lauum_padded(mfgp_ctx* h, const double* W, double* Kinv, int npad) {

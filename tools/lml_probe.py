@@ -22,3 +22,12 @@ for r in range(reps):
     lml, g, info, ms = ops.lml_grad(dX, dy, _ffi.KIND_COMPOSITE, 4, theta, buf, timed=True)
     print("N=%d rep %d lml=%.6f info=%d total=%.2f ms  stages(assemble,potrf,trtri,solve,lauum,grad)=%s" %
           (n, r, lml, info, ms.sum(), np.round(ms, 3)))
+if os.environ.get("MFGP_PROBE_CHECKSUM"):
+    # bit-level fingerprint of the factors and the gradient (A/B runs of schedule-only changes must agree exactly)
+    import hashlib
+    W = buf.W if hasattr(buf, "W") else None
+    parts = [np.asarray(g).tobytes(), np.float64(lml).tobytes()]
+    if W is not None:
+        parts.append(np.float64(W.double().sum().item()).tobytes())
+        parts.append(np.float64((W * W).sum().item()).tobytes())
+    print("checksum", hashlib.sha256(b"".join(parts)).hexdigest()[:16])
