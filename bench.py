@@ -273,6 +273,20 @@ def lml_grad_section(torch, pkg_ops, peaks, fp64_peak, n=16384, cpu=True):
         total += s.elapsed_time(e); stages += ms
     ms_eval = total / reps
     stages /= reps
+    # the Cholesky alone (mfgp_potrf on K_y assembled in place): inside an evaluation the inverse of the leading
+    # half overlaps the factorisation's tail, so stages_ms.potrf / .trtri split one overlapped region
+    potrf_alone = 0.0
+    for _ in range(reps):
+        K = pkg_ops.assemble(dX, _ffi.KIND_COMPOSITE, 4, theta)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        Wtmp, pinfo = pkg_ops.potrf(K)
+        e.record(); torch.cuda.synchronize()
+        # (mfgp_potrf copies the pivot status back: one sync; the W buffer is zero-filled by ops.potrf before the record)
+        potrf_alone += s.elapsed_time(e)
+        del K, Wtmp
+    potrf_alone /= reps
     names = ["assemble", "potrf", "trtri", "solve", "lauum", "grad_reduce"]
     hbm = peaks.get("hbm_gbs", 6650.0)
     asm_bytes = 4.0 * n * (n + 1) + 8.0 * n * 5          # lower triangle written + inputs read
@@ -288,8 +302,13 @@ def lml_grad_section(torch, pkg_ops, peaks, fp64_peak, n=16384, cpu=True):
         "roofline_eval": {"bound": "tensor", "achieved": n ** 3 / ms_eval / 1e9, "peak": fp64_peak,
                           "unit": "TFLOP/s", "frac": n ** 3 / ms_eval / 1e9 / fp64_peak,
                           "flops": float(n) ** 3},
-        "roofline_potrf": {"bound": "tensor", "achieved": n ** 3 / 3 / stages[1] / 1e9, "peak": fp64_peak,
-                           "unit": "TFLOP/s", "frac": n ** 3 / 3 / stages[1] / 1e9 / fp64_peak},
+        "potrf_alone_ms": potrf_alone,
+        "potrf_plus_trtri_ms": float(stages[1] + stages[2]),
+        "stages_note": "stages_ms.potrf ends where the factorisation is complete and includes the inverse of the "
+                       "leading half that ran under its tail (potrf_trtri_padded); potrf_alone_ms is mfgp_potrf by itself",
+        "roofline_potrf": {"bound": "tensor", "achieved": n ** 3 / 3 / potrf_alone / 1e9, "peak": fp64_peak,
+                           "unit": "TFLOP/s", "frac": n ** 3 / 3 / potrf_alone / 1e9 / fp64_peak,
+                           "ms": potrf_alone},
         "roofline_assemble": {"bound": "hbm", "achieved": asm_bytes / stages[0] / 1e6, "peak": hbm,
                               "unit": "GB/s", "frac": asm_bytes / stages[0] / 1e6 / hbm,
                               "bytes": asm_bytes, "note": "lower triangle only: 4N(N+1)+8ND",
@@ -794,8 +813,10 @@ def traffic_per_launch(nh, cols_per_launch):
     return per_col * cols_per_launch if per_col else None
 
 
-# profiles/r01_ncu_mc_hf_kernels_v6.txt: 1.651 GB for 75 776 columns at N_h = 1024
-TRAFFIC_BYTES_PER_COLUMN = {1024: 1.651e9 / 75776.0}
+# profiles/r02_ncu_mc_hf_kernels.txt (TMA kernel): 1.610 GB read + 0.008 GB written for 75 776 columns at N_h = 1024
+# (algorithmic: 0.621 GB of Ks + the 4.2 MB lower triangle of W; every CTA re-reads its Ks tile for each of the
+# 8 row tiles of W and 148 resident 1 MB tiles exceed L2 -- at 8.6 % of DRAM throughput this is not the limiter)
+TRAFFIC_BYTES_PER_COLUMN = {1024: 1.618e9 / 75776.0}
 
 
 if __name__ == "__main__":
