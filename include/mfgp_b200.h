@@ -176,6 +176,12 @@ int mfgp_augment(mfgp_handle_t h, const mfgp_level_t* lf, const double* d_X, lon
  * d_eps: (M, S) standard normals, or NULL -> Philox4x32-10 keyed by seed, counter = (m0+m)*S+s.
  * d_weights: optional (M,) quadrature weights; h_wsum[0] += sum_m w_m mean_m (PCE mean).
  * E = 1 (NARGP: offsets = {0}) only; mfgp_predict_mc_delays handles E > 1. */
+/* Recommended scratch for mfgp_predict_mc / mfgp_predict_mc_chain.  N_up = the largest training-set size among
+ * the upper levels.  Upper levels with N <= 64 -- the reference's own sizes, src/gpc/mfgp_gpc.py:10,18-20 -- run a
+ * fused generator + contraction kernel that keeps no cross-covariance row, so the scratch then holds three
+ * doubles per (point, sample) column and whole batches go through in one launch; otherwise a chunk is four
+ * 128-column tiles per SM of (padded N_up + d + 4) doubles per column.  Results never depend on the size. */
+size_t mfgp_predict_mc_ws_bytes(int N_l, int N_up, int d, long long M, int S);
 int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,
                     const double* d_Xtest, long long M, int S, const double* d_eps,
                     unsigned long long seed, long long m0, int include_lf_noise,

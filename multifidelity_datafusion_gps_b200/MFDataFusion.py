@@ -269,10 +269,8 @@ class MultifidelityDataFusion(AbstractMFGP):
         npl, nph, d = self.lf_model.npad, self.hf_model.npad, self.input_dim
         if E == 1:
             if ws_bytes is None:
-                per_col = (nph + d + 4) * 8               # Ks row + [x, z] + mean, sum of squares, sample
-                want = 16 * M + 148 * 128 * 4 * per_col
-                need = 16 * M + max((S + 256) * per_col, (npl + 1) * 128 * 8) + 4096
-                ws_bytes = max(min(want, 12 << 30), need)     # ~4 column tiles per SM up to N_h = 16384
+                # ~4 column tiles per SM up to N_h = 16384; three doubles per column for N_h <= 64 (fused kernel)
+                ws_bytes = h.lib.mfgp_predict_mc_ws_bytes(self.lf_model.N, self.hf_model.N, d, M, S)
             ws = gp.workspace(self.device, ws_bytes)
             h.check(h.lib.mfgp_predict_mc(
                 h.h, ctypes.byref(lf), ctypes.byref(hf), dX.data_ptr(), M, S,

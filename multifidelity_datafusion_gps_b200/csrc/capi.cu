@@ -38,6 +38,12 @@ int append_point_launch(mfgp_ctx* h, const double* k, int N, int npad, double ka
 int mc_max_samples();
 int predict_configure(mfgp_ctx* h);
 int sqrt_launch(mfgp_ctx* h, double* v, long long n);
+int mc_small_applies(int N);
+int mc_small_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int npad, const double* W,
+                    const double* alpha, const double* Xtest, const double* mu_l, const double* sd_l,
+                    const double* eps, unsigned long long seed, long long m_global0, long long m_lo,
+                    long long npts, int S, double* mu_c, double* ss, const double* zcol, long long z_off,
+                    long long ldz, int* took);
 int mc_aggregate_launch(mfgp_ctx* h, const double* mu_c, const double* v_c, long long npts, int S,
                         double* mean, double* var);
 int argmax_launch(mfgp_ctx* h, const double* v, long long n, double* d_val, long long* d_idx);
@@ -669,15 +675,19 @@ static int mc_chain_impl(mfgp_ctx* h, const mfgp_level_t* const* levels, int L, 
   if (trace) cudaEventRecord(h->ev[1], h->stream);
   // upper levels over (point, sample) columns
   const int D = d + 1;
-  const long long per_col = (long long)npad_max + D + 3;
-  long long max_cols = whole_waves(restd / per_col / 128 * 128);
-  ARG_CHECK(h, max_cols >= 128);
+  // when every upper level takes the fused small-level kernel no cross-covariance row is ever stored: a column
+  // needs its mean, sum of squares and sample only, and a chunk is as many points as the scratch holds
+  bool all_small = true;
+  for (int t = 1; t < L; t++) all_small = all_small && mc_small_applies(levels[t]->N);
+  const long long per_col = all_small ? 3 : (long long)npad_max + D + 3;
+  long long max_cols = all_small ? (restd - 384) / per_col : whole_waves(restd / per_col / 128 * 128);
+  ARG_CHECK(h, max_cols >= (all_small ? S : 128));
   long long pm = max_cols / S;
   ARG_CHECK(h, pm >= 1);   // the scratch must hold all S samples of at least one point
   if (pm > M) pm = M;
   const long long cp_max = (pm * S + 127) / 128 * 128;
   double* Xq = rest;                 // (cp_max, D): rows [x, z] when S exceeds the generator's sample limit
-  double* mu_c = Xq + cp_max * D;
+  double* mu_c = Xq + (all_small ? 0 : cp_max * D);
   double* ss = mu_c + cp_max;
   double* zcol = ss + cp_max;
   double* Ks = zcol + cp_max;
@@ -690,8 +700,13 @@ static int mc_chain_impl(mfgp_ctx* h, const mfgp_level_t* const* levels, int L, 
       const int npad = mfgp_padded_n(lv->N);
       const unsigned long long key = seed + (unsigned long long)(t - 1) * 0x9E3779B97F4A7C15ULL;
       const double* eps_t = d_eps ? d_eps + (long long)(t - 1) * M * S : nullptr;
+      int fused = 0;
       if (t == 1) {
-        if (S <= mc_max_samples()) {
+        if ((rc = mc_small_launch(h, kp[1], lv->d_X, lv->N, npad, lv->d_W, lv->d_alpha, d_Xtest, mu_l, sd_l, eps_t, key,
+                                  m0, m_lo, npts, S, mu_c, ss, nullptr, 0, 0, &fused)))
+          return rc;
+        if (fused) {
+        } else if (S <= mc_max_samples()) {
           // one CTA per test point: x-dependent kernel factors shared by its S samples (1 exp / element)
           if ((rc = cross_gen_mc_launch(h, kp[1], lv->d_X, lv->N, npad, lv->d_alpha, d_Xtest, mu_l, sd_l, eps_t,
                                         key, m0, m_lo, npts, S, cols_pad, Ks, mu_c, nullptr, 0, 0)))
@@ -705,11 +720,15 @@ static int mc_chain_impl(mfgp_ctx* h, const mfgp_level_t* const* levels, int L, 
       } else {
         // z = mu + sqrt(v) eps of the level below, per (point, sample) column, then this level at [x, z]
         if ((rc = sample_cols_launch(h, mu_c, ss, eps_t, key, m0, m_lo, ncols, S, zcol))) return rc;
-        if ((rc = cross_gen_mc_launch(h, kp[t], lv->d_X, lv->N, npad, lv->d_alpha, d_Xtest, nullptr, nullptr,
+        if ((rc = mc_small_launch(h, kp[t], lv->d_X, lv->N, npad, lv->d_W, lv->d_alpha, d_Xtest, nullptr, nullptr,
+                                  nullptr, 0, m0, m_lo, npts, S, mu_c, ss, zcol, 0, S, &fused)))
+          return rc;
+        if (!fused &&
+            (rc = cross_gen_mc_launch(h, kp[t], lv->d_X, lv->N, npad, lv->d_alpha, d_Xtest, nullptr, nullptr,
                                       nullptr, 0, m0, m_lo, npts, S, cols_pad, Ks, mu_c, zcol, 0, S)))
           return rc;
       }
-      if ((rc = trmm_sumsq(h, lv->d_W, npad, Ks, cols_pad, ss))) return rc;
+      if (!fused && (rc = trmm_sumsq(h, lv->d_W, npad, Ks, cols_pad, ss))) return rc;
       const int with_noise = (t == L - 1) ? include_top_noise : include_lower_noise;
       if ((rc = finish_var_launch(h, ss, ncols, kp[t].kdiag, with_noise ? kp[t].noise : 0.0, ss))) return rc;
     }
@@ -730,6 +749,26 @@ static int mc_chain_impl(mfgp_ctx* h, const mfgp_level_t* const* levels, int L, 
     h_wsum[0] += h->h_pinned[20];
   }
   return 0;
+}
+
+size_t mfgp_predict_mc_ws_bytes(int N_l, int N_up, int d, long long M, int S) {
+  const long long npl = mfgp_padded_n(N_l), npu = mfgp_padded_n(N_up);
+  const long long tiles4 = (long long)MFGP_NUM_SMS * 128 * 4;
+  const long long lf_need = (npl + 1) * 128 * 8, lf_want = (npl + 1) * tiles4 * 8;
+  long long up_need, up_want;
+  if (mc_small_applies(N_up)) {
+    const long long cols = M * (long long)S;
+    up_need = ((long long)S + 256) * 24;
+    up_want = (cols < (1LL << 28) ? cols : (1LL << 28)) * 24 + 8192;
+  } else {
+    const long long per_col = (npu + d + 4) * 8;
+    up_need = ((long long)S + 256) * per_col;
+    up_want = tiles4 * per_col;
+  }
+  const long long need = 16 * M + (lf_need > up_need ? lf_need : up_need) + 4096;
+  long long want = 16 * M + (lf_want > up_want ? lf_want : up_want) + 4096;
+  if (want > (12LL << 30)) want = 12LL << 30;
+  return (size_t)(want > need ? want : need);
 }
 
 int mfgp_predict_mc(mfgp_handle_t h, const mfgp_level_t* lf, const mfgp_level_t* hf,

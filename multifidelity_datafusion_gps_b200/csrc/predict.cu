@@ -4,6 +4,7 @@
 // src/abstractMFGP.py:104): the cross-covariance block is generated on the fly in column chunks
 // (never an N x M matrix in HBM beyond one chunk), the mean is reduced while it is generated, and
 // the variance comes from tmp = W Kx as a DMMA GEMM with a fused column sum-of-squares epilogue.
+#include <stdlib.h>
 #include "common.cuh"
 #include "fastmath.cuh"
 
@@ -295,6 +296,137 @@ __global__ void __launch_bounds__(256)
   for (int s = tid; s < S; s += 256) mu_c[(long long)blockIdx.x * S + s] = macc[s];
 }
 
+
+// ---- K7 for small upper levels (N <= 64): generator AND contraction in one kernel, nothing N-wide in HBM ----
+// The reference's own high-fidelity levels hold 5-30 points (src/gpc/mfgp_gpc.py:10,18-20).  Through the
+// general path a (point, sample) column of such a level costs a 128-wide row of Ks written to HBM and read
+// back, and a 128 x 128 triangular product: at N = 30 that is (128/30)^2 = 18 times the algorithmic flops.
+// Here ONE WARP owns a test point: the x-dependent factors of its S columns go to the warp's slice of shared
+// memory once (as in cross_gen_mc_kernel), the columns are taken eight at a time as the n dimension of
+// DMMA.8x8x4, the lane that owns B[k = 4 kk + t][n = g] COMPUTES that cross-covariance element (one exp2s) in
+// the register the tensor instruction reads, and the NP x NP leading block of W = L^-1 (NP = 16, 32 or 64) sits in
+// registers as A fragments for the whole kernel (6 / 20 / 72 doubles per lane; only blocks with k <= row).
+// Per column: N exponentials and NP^2/2 multiply-adds, no shared-memory traffic in the product, no barrier.
+// All reductions in fixed order; a column's result does not depend on how points are split over launches.
+__device__ __forceinline__ void dmma884p(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int MCS_WARPS = 8;
+
+template <int NP>
+__global__ void __launch_bounds__(MCS_WARPS * 32, NP <= 32 ? 2 : 1)
+    mc_small_kernel(KParams kp, const double* __restrict__ X, int N, int ldw, const double* __restrict__ W,
+                    const double* __restrict__ alpha, const double* __restrict__ Xtest,
+                    const double* __restrict__ mu_l, const double* __restrict__ sd_l,
+                    const double* __restrict__ eps, unsigned long long seed, long long m_global0, long long m_lo,
+                    long long npts, int S, double* __restrict__ mu_c, double* __restrict__ ss_out,
+                    const double* __restrict__ zcol, long long z_off, long long ldz) {
+  constexpr int RB = NP / 8, KS = NP / 4;                // row blocks, k steps
+  extern __shared__ __align__(16) double sm_mcs[];       // tbl[256] | sz[NP] | sa[NP] | sX[d][NP] | per warp: su[NP], sv[NP]
+  const int d = kp.d;                                    // D = d + 1
+  double* stbl = sm_mcs;
+  double* sz = stbl + 256;
+  double* sa = sz + NP;
+  double* sX = sa + NP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  double* su = sX + d * NP + warp * 2 * NP;
+  double* sv = su + NP;
+  stbl[tid] = kp.exp_tbl[tid];
+  for (int idx = tid; idx < NP * (d + 1); idx += MCS_WARPS * 32) {
+    const int j = idx / (d + 1), dd = idx - j * (d + 1);
+    const double v = j < N ? X[idx] : 0.0;
+    if (dd < d) sX[dd * NP + j] = v;
+    else sz[j] = v;
+  }
+  if (tid < NP) sa[tid] = tid < N ? alpha[tid] : 0.0;
+  // A fragments: wf[r][kk] = W[8 r + g][4 kk + t] for the blocks that touch the lower triangle (kk <= 2 r + 1)
+  double wf[RB][KS];
+#pragma unroll
+  for (int r = 0; r < RB; r++)
+#pragma unroll
+    for (int kk = 0; kk < KS; kk++)
+      if (kk <= 2 * r + 1) wf[r][kk] = W[(long)(8 * r + g) * ldw + 4 * kk + t];
+  __syncthreads();
+  const unsigned tbl = (unsigned)__cvta_generic_to_shared(stbl);
+  const double uz = kp.uz;
+  const bool has3 = kp.s3 != 0.0;
+  for (long long pl = (long long)blockIdx.x * MCS_WARPS + warp; pl < npts; pl += (long long)gridDim.x * MCS_WARPS) {
+    const long long m = m_lo + pl;
+    // x-dependent factors of this point, one training point per lane
+    __syncwarp();
+#pragma unroll
+    for (int j0 = 0; j0 < NP; j0 += 32) {
+      const int j = j0 + lane;
+      if (NP < 32 && j >= NP) break;
+      double rx = 0.0;
+      for (int dd = 0; dd < d; dd++) {
+        const double q = Xtest[m * d + dd] - sX[dd * NP + j];
+        rx = fma(q, q, rx);
+      }
+      su[j] = fma(kp.ux, rx, kp.lc12);
+      sv[j] = has3 ? fm::exp2s_flat(fma(kp.u3, rx, kp.ls3), tbl) : 0.0;
+    }
+    __syncwarp();
+    const double mul = mu_l ? mu_l[m] : 0.0, sdl = sd_l ? sd_l[m] : 1.0;
+    for (int s0 = 0; s0 < S; s0 += 32) {
+      // the samples of 32 columns, one per lane (same draws as cross_gen_mc_kernel)
+      double zl = 0.0;
+      if (s0 + lane < S) {
+        const int sidx = s0 + lane;
+        if (zcol) {
+          zl = mul + zcol[(z_off + pl) * ldz + sidx];
+        } else {
+          const double e = eps ? eps[m * S + sidx]
+                               : philox_normal((unsigned long long)((m_global0 + m) * S + sidx), seed);
+          zl = fma(sdl, e, mul);
+        }
+      }
+      const int ngrp = min(4, (S - s0 + 7) >> 3);
+      for (int grp = 0; grp < ngrp; grp++) {
+        const double zc = __shfl_sync(0xffffffffu, zl, 8 * grp + g);     // sample of column g of this group
+        double D0[RB], D1[RB];
+#pragma unroll
+        for (int r = 0; r < RB; r++) D0[r] = D1[r] = 0.0;
+        double macc = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < KS; kk++) {
+          const int j = 4 * kk + t;
+          const double q = zc - sz[j];
+          double b = fm::exp2s_flat(fma(uz * q, q, su[j]), tbl) + sv[j];
+          if (j >= N) b = 0.0;                                           // identity pad: exactly zero
+          macc = fma(b, sa[j], macc);
+#pragma unroll
+          for (int r = kk / 2; r < RB; r++) dmma884p(D0[r], D1[r], wf[r][kk], b);
+        }
+        // column sums of squares: rows 8 r + g of columns 2 t, 2 t + 1; then over g
+        double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+          q0 = fma(D0[r], D0[r], q0);
+          q1 = fma(D1[r], D1[r], q1);
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+          q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+        }
+        macc += __shfl_xor_sync(0xffffffffu, macc, 1);
+        macc += __shfl_xor_sync(0xffffffffu, macc, 2);
+        const long long c0 = pl * S + s0 + 8 * grp;
+        const int left = S - s0 - 8 * grp;                               // valid columns in this group
+        if (g == 0) {
+          if (2 * t < left) ss_out[c0 + 2 * t] = q0;
+          if (2 * t + 1 < left) ss_out[c0 + 2 * t + 1] = q1;
+        }
+        if (t == 0 && g < left) mu_c[c0 + g] = macc;
+      }
+    }
+  }
+}
 
 // ---- K7 with delays: joint low-fidelity posterior at the E augmented locations of a test point ----
 // G[p][a,b] = sum_i T[i][p*E+a] * T[i][p*E+b]  (packed lower triangle, a >= b); eight threads per point
@@ -879,6 +1011,48 @@ int cross_gen_mc_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, 
     zero_rows_kernel<<<nblk(tail, 256), 256, 0, h->stream>>>(Ks + npts * S * npad, tail);
     LAUNCH_CHECK(h);
   }
+  return 0;
+}
+
+int mc_small_applies(int N) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("MFGP_MC_SMALL");
+    enabled = e ? (atoi(e) != 0) : 1;
+  }
+  return enabled && N <= 64;
+}
+
+// Fused generator + contraction for an upper level with N <= 64 (see mc_small_kernel).  Writes mu_c and the raw
+// column sums of squares of the npts * S columns; returns 0 without launching (and *took = 0) when the level does
+// not qualify.  MFGP_MC_SMALL=0 switches the path off.
+int mc_small_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int npad, const double* W,
+                    const double* alpha, const double* Xtest, const double* mu_l, const double* sd_l,
+                    const double* eps, unsigned long long seed, long long m_global0, long long m_lo,
+                    long long npts, int S, double* mu_c, double* ss, const double* zcol, long long z_off,
+                    long long ldz, int* took) {
+  *took = 0;
+  if (!mc_small_applies(N) || npts <= 0) return 0;
+  const int NP = N <= 16 ? 16 : (N <= 32 ? 32 : 64);
+  const size_t smem = (size_t)(256 + 2 * NP + kp.d * NP + MCS_WARPS * 2 * NP) * sizeof(double);
+  const long long want = (npts + MCS_WARPS - 1) / MCS_WARPS;
+  // exactly the resident CTAs: a warp walks over its share of the points, so the CTA's set-up (exp table, training
+  // inputs, W fragments) is paid once per launch
+  const long long cap = (long long)MFGP_NUM_SMS * (NP <= 32 ? 2 : 1);
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  prof_begin(h, PC_TRMM_SUMSQ);
+  if (NP == 16)
+    mc_small_kernel<16><<<grid, MCS_WARPS * 32, smem, h->stream>>>(kp, X, N, npad, W, alpha, Xtest, mu_l, sd_l, eps, seed,
+                                                                  m_global0, m_lo, npts, S, mu_c, ss, zcol, z_off, ldz);
+  else if (NP == 32)
+    mc_small_kernel<32><<<grid, MCS_WARPS * 32, smem, h->stream>>>(kp, X, N, npad, W, alpha, Xtest, mu_l, sd_l, eps, seed,
+                                                                  m_global0, m_lo, npts, S, mu_c, ss, zcol, z_off, ldz);
+  else
+    mc_small_kernel<64><<<grid, MCS_WARPS * 32, smem, h->stream>>>(kp, X, N, npad, W, alpha, Xtest, mu_l, sd_l, eps, seed,
+                                                                  m_global0, m_lo, npts, S, mu_c, ss, zcol, z_off, ldz);
+  prof_end(h, PC_TRMM_SUMSQ);
+  LAUNCH_CHECK(h);
+  *took = 1;
   return 0;
 }
 

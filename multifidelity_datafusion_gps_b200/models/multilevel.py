@@ -96,10 +96,8 @@ class MultiLevelNARGP:
         mean = torch.empty(M, dtype=torch.float64, device=dX.device)
         var = torch.empty(M, dtype=torch.float64, device=dX.device)
         wsum = ctypes.c_double(0.0) if d_weights is not None else None
-        nph = max(g.npad for g in gps[1:])
-        per_col = (nph + self.input_dim + 4) * 8
-        need = 16 * M + max((S + 256) * per_col, (gps[0].npad + 1) * 128 * 8) + 4096
-        ws = gp.workspace(top.device, max(min(16 * M + 148 * 128 * 4 * per_col, 12 << 30), need))
+        ws = gp.workspace(top.device, h.lib.mfgp_predict_mc_ws_bytes(gps[0].N, max(g.N for g in gps[1:]),
+                                                                     self.input_dim, M, S))
         h.check(h.lib.mfgp_predict_mc_chain(
             h.h, ctypes.cast(ptrs, ctypes.c_void_p), L, dX.data_ptr(), M, S,
             d_eps.data_ptr() if d_eps is not None else None, int(seed), int(m0), int(include_lower_noise), 1,

@@ -360,6 +360,20 @@ def test_mc_propagation_matches_oracle_with_supplied_normals(pkg):
     assert util.rel_err(var, var_ref, 1.1) < 1e-6
 
 
+@pytest.mark.parametrize("n_h,S", [(5, 100), (16, 9), (17, 40), (30, 7), (32, 33), (33, 100), (64, 9), (65, 100), (96, 40)])
+def test_mc_propagation_across_the_fused_small_level_boundary(pkg, n_h, S):
+    """N_h <= 16, <= 32 and <= 64 take the fused generator + contraction kernel (mc_small_kernel<16 / 32 / 64>), larger levels
+    the general Ks + trmm_sumsq pair; ragged sample counts exercise the partial 8-column groups."""
+    m, o = _mc_models(pkg, n_l=60, n_h=n_h, seed=11)
+    M = 137
+    Xt = np.random.default_rng(8).uniform(size=(M, 4))
+    eps = np.random.default_rng(3).standard_normal((M, S, 1))
+    mean, var = m.predict_mc(Xt, n_samples=S, eps=eps)
+    mu_ref, var_ref = o.predict_mc(Xt, eps)
+    assert util.rel_err(mean, mu_ref) < 1e-8
+    assert util.rel_err(var, var_ref, 1.1) < 1e-6
+
+
 def test_mc_one_sample_zero_eps_reproduces_predict(pkg):
     # SURVEY.md section 8a row A8: S = 1, eps = 0 must reproduce the reference predict()
     m, o = _mc_models(pkg)
