@@ -163,6 +163,21 @@ int mfgp_predict_small(mfgp_handle_t h, const mfgp_level_t* hf, const mfgp_level
                        int M, const double* h_offsets, int E, double tau, int include_noise, double* h_mean,
                        double* h_var);
 
+/* K6, resident form of the latency path ("point service").  The reference's default acquisition asks for up to
+ * 20 000 single-point predicts in sequence, each answer deciding the next question
+ * (src/adaptation_maximizers/scipydirect_wrapper.py:22-26 -> src/MFDataFusion.py:153-156).  _start puts ONE CTA
+ * on the device that stays resident and answers questions posted through mapped pinned host memory; _eval posts
+ * one row (lf != NULL at _start: plain inputs (lf->D); lf == NULL: an augmented row (hf->D)) and spins on the
+ * answer (h_out[0] = mean, h_out[1] = variance; bit-identical to mfgp_predict_small); _stop releases the SM.
+ * No launch and no stream synchronisation per question.  The kernel leaves by itself after idle_ms (<= 0: 20 ms)
+ * without a question and is relaunched transparently by the next _eval (_relaunches counts these).  The factors
+ * of hf / lf must not change between _start and _stop.  One service per handle; _eval is not re-entrant. */
+int mfgp_point_service_start(mfgp_handle_t h, const mfgp_level_t* hf, const mfgp_level_t* lf,
+                             const double* h_offsets, int E, double tau, int include_noise, double idle_ms);
+int mfgp_point_service_eval(mfgp_handle_t h, const double* h_x, double* h_out);
+int mfgp_point_service_stop(mfgp_handle_t h);
+long long mfgp_point_service_relaunches(mfgp_handle_t h);
+
 /* A1 with a data-driven low-fidelity level.  Replaces __augment_Data (src/MFDataFusion.py:177-208)
  * when f_low is lf_model.predict(.)[0] (src/abstractMFGP.py:104):
  * Xaug[i] = [x_i, mu_l(x_i + o_0 tau), ..., mu_l(x_i + o_{E-1} tau)].  h_offsets: HOST (E, d). */

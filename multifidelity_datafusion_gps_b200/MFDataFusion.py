@@ -145,6 +145,62 @@ class MultifidelityDataFusion(AbstractMFGP):
         h.check(rc)
         return mean[:, None], var[:, None]
 
+    # -- resident form of predict_point: what the default DIRECT maximiser drives ---------------------------
+    def point_service_start(self, idle_ms=20.0):
+        """Put the single-row predictor on the device as a RESIDENT kernel (mfgp_point_service_start) for a run
+        of sequential single-point questions -- the reference's default acquisition asks up to 20 000 of them,
+        each depending on the previous answer (src/adaptation_maximizers/scipydirect_wrapper.py:22-26).
+        Returns False (nothing started) for shapes the service does not take; pair with point_service_stop()."""
+        h = _ffi.get_handle(self.device)
+        E = self.augm_iterator.new_entries_count()
+        if (getattr(self.f_low, "device_predict", None) is not None or self.hf_model.N > 2048
+                or self.input_dim + E > 64 or E * self.input_dim > 96):
+            return False
+        self._apply_add_noise()
+        self.hf_model._ensure_posterior()
+        self._svc_levels = [self.hf_model.level_struct()]           # keep the structs alive while the kernel runs
+        offs = np.ascontiguousarray(self.augm_iterator.offset_table(), dtype=np.float64)
+        if self.data_driven_lf_approach:
+            self.lf_model._ensure_posterior()
+            self._svc_levels.append(self.lf_model.level_struct())
+            h.check(h.lib.mfgp_point_service_start(h.h, ctypes.byref(self._svc_levels[0]),
+                                                   ctypes.byref(self._svc_levels[1]), offs.ctypes.data, E,
+                                                   float(self.tau), 1, float(idle_ms)))
+            self._svc_x = np.empty(self.input_dim)
+        else:
+            h.check(h.lib.mfgp_point_service_start(h.h, ctypes.byref(self._svc_levels[0]), None, None, 0, 0.0, 1,
+                                                   float(idle_ms)))
+            self._svc_x = np.empty(self.input_dim + E)
+        self._svc_offs_tau = offs * self.tau
+        self._svc_out = np.empty(2)
+        self._svc_call = (h.lib.mfgp_point_service_eval, h.h, self._svc_x.ctypes.data, self._svc_out.ctypes.data)
+        self._svc_handle = h
+        return True
+
+    def point_service_eval(self, x):
+        """(mean, variance) at ONE input x (input_dim,), through the resident kernel; bit-identical to
+        predict_point(x[None])."""
+        fn, hh, px, po = self._svc_call
+        d = self.input_dim
+        if self.data_driven_lf_approach:
+            self._svc_x[:] = x
+        else:
+            self._svc_x[:d] = x
+            # one call of the user's low-fidelity function per (E, d) group, as the reference makes it
+            # (src/MFDataFusion.py:197)
+            self._svc_x[d:] = np.asarray(self.f_low(np.asarray(x)[None, :] + self._svc_offs_tau)).ravel()
+        rc = fn(hh, px, po)
+        if rc:
+            self._svc_handle.check(rc)
+        return self._svc_out[0], self._svc_out[1]
+
+    def point_service_stop(self):
+        h = getattr(self, "_svc_handle", None)
+        if h is not None:
+            h.check(h.lib.mfgp_point_service_stop(h.h))
+            self._svc_handle = None
+            self._svc_levels = None
+
     def _apply_add_noise(self):
         if self.add_noise:                                  # :154-155: re-inference at noise 1e-6
             if self.hf_model.likelihood.variance != 1e-6:

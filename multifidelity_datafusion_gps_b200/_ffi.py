@@ -22,7 +22,7 @@ EXPORTS = [
     "mfgp_version", "mfgp_padded_n", "mfgp_create", "mfgp_destroy", "mfgp_set_stream",
     "mfgp_last_error", "mfgp_launch_count", "mfgp_profile_enable", "mfgp_profile_read", "mfgp_assemble", "mfgp_factorize", "mfgp_lml_grad",
     "mfgp_lml_grad_timed", "mfgp_lml_grad_batch_max", "mfgp_lml_grad_batch", "mfgp_append_point", "mfgp_potrf", "mfgp_trtri", "mfgp_lauum", "mfgp_predict_ws_bytes",
-    "mfgp_predict", "mfgp_predict_small_max_rows", "mfgp_predict_small", "mfgp_augment", "mfgp_predict_mc_ws_bytes", "mfgp_predict_mc", "mfgp_predict_mc_chain", "mfgp_predict_mc_joint_ws_bytes", "mfgp_predict_mc_joint",
+    "mfgp_predict", "mfgp_predict_small_max_rows", "mfgp_predict_small", "mfgp_point_service_start", "mfgp_point_service_eval", "mfgp_point_service_stop", "mfgp_point_service_relaunches", "mfgp_augment", "mfgp_predict_mc_ws_bytes", "mfgp_predict_mc", "mfgp_predict_mc_chain", "mfgp_predict_mc_joint_ws_bytes", "mfgp_predict_mc_joint",
     "mfgp_predict_mc_delays", "mfgp_fill_normal",
     "mfgp_argmax", "mfgp_pce_ws_bytes", "mfgp_pce_project",
 ]
@@ -93,6 +93,12 @@ def load_library():
                                     vp, c_ull, c_ll, c_int, c_int, vp, vp, vp, vp, vp, c_sz]
     lib.mfgp_predict_mc_chain.argtypes = [vp, vp, c_int, vp, c_ll, c_int, vp, c_ull, c_ll, c_int, c_int, vp, vp,
                                           vp, vp, vp, c_sz]
+    lib.mfgp_point_service_start.argtypes = [vp, ctypes.POINTER(Level), ctypes.POINTER(Level), vp, c_int, c_dbl, c_int,
+                                             c_dbl]
+    lib.mfgp_point_service_eval.argtypes = [vp, vp, vp]
+    lib.mfgp_point_service_stop.argtypes = [vp]
+    lib.mfgp_point_service_relaunches.argtypes = [vp]
+    lib.mfgp_point_service_relaunches.restype = c_ll
     lib.mfgp_predict_mc_ws_bytes.argtypes = [c_int, c_int, c_int, c_ll, c_int]
     lib.mfgp_predict_mc_ws_bytes.restype = c_sz
     lib.mfgp_predict_mc_joint_ws_bytes.argtypes = [c_int, c_int, c_ll, c_int]
@@ -110,7 +116,7 @@ def load_library():
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("mfgp_last_error", "mfgp_launch_count", "mfgp_predict_ws_bytes", "mfgp_pce_ws_bytes",
-                        "mfgp_predict_mc_joint_ws_bytes", "mfgp_predict_mc_ws_bytes"):
+                        "mfgp_predict_mc_joint_ws_bytes", "mfgp_predict_mc_ws_bytes", "mfgp_point_service_relaunches"):
             fn.restype = c_int
     _lib = lib
     return lib

@@ -21,15 +21,27 @@ class ScipyDirectMaximizer(AbstractMaximizer):
         from scipy.optimize import direct
         bound = [(lower_bound[i], upper_bound[i]) for i in range(len(lower_bound))]
 
-        # a model of this package evaluates single points through its latency path (one launch, one sync)
+        # A model of this package answers the search's sequential single-point questions from a kernel that stays
+        # RESIDENT for the duration of the search (no launch, no synchronisation per question); shapes the
+        # service does not take go through the latency path (one or two launches, one sync per question).
         owner = getattr(model_predict, "__self__", None)
-        if owner is not None and getattr(model_predict, "__name__", "") == "predict" and hasattr(owner, "predict_point"):
-            model_predict = owner.predict_point
+        is_own = (owner is not None and getattr(model_predict, "__name__", "") == "predict"
+                  and hasattr(owner, "predict_point"))
+        service = bool(is_own and hasattr(owner, "point_service_start") and owner.point_service_start())
+        if service:
+            def acquisition_curve(x):
+                return -float(owner.point_service_eval(x)[1])
+        else:
+            if is_own:
+                model_predict = owner.predict_point
 
-        def acquisition_curve(x):
-            _, uncertainty = model_predict(np.asarray(x)[None])
-            return -float(np.asarray(uncertainty).ravel()[0])
-
-        res = direct(acquisition_curve, bound, eps=self.eps, maxfun=self.maxf, maxiter=self.maxT,
-                     locally_biased=False, vol_tol=0.0, len_tol=0.0)
+            def acquisition_curve(x):
+                _, uncertainty = model_predict(np.asarray(x)[None])
+                return -float(np.asarray(uncertainty).ravel()[0])
+        try:
+            res = direct(acquisition_curve, bound, eps=self.eps, maxfun=self.maxf, maxiter=self.maxT,
+                         locally_biased=False, vol_tol=0.0, len_tol=0.0)
+        finally:
+            if service:
+                owner.point_service_stop()
         return res.x, res.fun

@@ -1,6 +1,7 @@
 // extern "C" entry points declared in include/mfgp_b200.h: argument checks, scratch layout,
 // chunk loops and stream ordering.  No torch types, no allocation outside mfgp_create.
 #include <stdlib.h>
+#include <time.h>
 #include "common.cuh"
 
 // launchers defined in predict.cu
@@ -55,6 +56,7 @@ int build_mc_rows_joint_launch(mfgp_ctx* h, const double* Xtest, const double* m
                                long long m_lo, long long ncols, int S, int d, int E, double* out);
 int wdot_launch(mfgp_ctx* h, const double* w, const double* x, long long n, double* d_out);
 int predict_small_max_n();
+int point_service_launch(mfgp_ctx* h, const PointServiceArgs& a, PointServiceCtl* d_ctl, cudaStream_t stream);
 int predict_small_launch(mfgp_ctx* h, const KParams& kh, const mfgp_level_t* hf, const KParams* kl,
                          const mfgp_level_t* lf, const double* Xq, int M, const double* d_offs, int E, double tau,
                          double* Xaug_tmp, double noise_add, double* out);
@@ -216,7 +218,11 @@ int mfgp_create(int device, mfgp_handle_t* out) {
     int pr_least = 0, pr_greatest = 0;
     ok = cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest) == cudaSuccess &&
          cudaStreamCreateWithPriority(&h->s_hi, cudaStreamNonBlocking, pr_greatest) == cudaSuccess &&
-         cudaStreamCreateWithPriority(&h->s_mid, cudaStreamNonBlocking, (pr_least + pr_greatest) / 2) == cudaSuccess;
+         cudaStreamCreateWithPriority(&h->s_mid, cudaStreamNonBlocking, (pr_least + pr_greatest) / 2) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&h->s_svc, cudaStreamNonBlocking, pr_greatest) == cudaSuccess &&
+         cudaHostAlloc(&h->svc_h, sizeof(PointServiceCtl), cudaHostAllocMapped) == cudaSuccess &&
+         cudaHostGetDevicePointer((void**)&h->svc_d, h->svc_h, 0) == cudaSuccess;
+    if (ok) memset(h->svc_h, 0, sizeof(PointServiceCtl));
   }
   if (ok) ok = cudaMemset(h->d_info, 0, 4 * sizeof(int)) == cudaSuccess;
   if (ok) {   // 2^(j/256) rounded from 64-bit-mantissa long double
@@ -248,6 +254,12 @@ int mfgp_destroy(mfgp_handle_t h) {
   for (int i = 0; i < 3 * 64 + 4; i++) cudaEventDestroy(h->ev_la[i]);
   if (h->s_hi) cudaStreamDestroy(h->s_hi);
   if (h->s_mid) cudaStreamDestroy(h->s_mid);
+  if (h->svc_active) {
+    h->svc_h->stop = 1;
+    cudaStreamSynchronize(h->s_svc);
+  }
+  if (h->s_svc) cudaStreamDestroy(h->s_svc);
+  if (h->svc_h) cudaFreeHost(h->svc_h);
   if (h->prof_ev) {
     for (int i = 0; i < MFGP_PROF_CLASSES * MFGP_PROF_POOL * 2; i++) cudaEventDestroy(h->prof_ev[i]);
     delete[] h->prof_ev;
@@ -592,6 +604,99 @@ int mfgp_predict_small(mfgp_handle_t h, const mfgp_level_t* hf, const mfgp_level
   }
   return 0;
 }
+
+// ---- point service (see point_service_kernel) ----------------------------------------------------------
+static int point_service_relaunch(mfgp_ctx* h) {
+  h->svc_h->alive = 1;
+  h->svc_args.start_seq = h->svc_h->ack_seq;
+  __sync_synchronize();
+  return point_service_launch(h, h->svc_args, h->svc_d, h->s_svc);
+}
+
+int mfgp_point_service_stop(mfgp_handle_t h) {
+  ENTER(h);
+  if (!h->svc_active) return 0;
+  h->svc_h->stop = 1;
+  __sync_synchronize();
+  CUDA_TRY(h, cudaStreamSynchronize(h->s_svc));
+  h->svc_active = 0;
+  return 0;
+}
+
+int mfgp_point_service_start(mfgp_handle_t h, const mfgp_level_t* hf, const mfgp_level_t* lf,
+                             const double* h_offsets, int E, double tau, int include_noise, double idle_ms) {
+  ENTER(h);
+  int rc;
+  if (h->svc_active && (rc = mfgp_point_service_stop(h))) return rc;
+  PointServiceArgs& a = h->svc_args;
+  memset(&a, 0, sizeof(a));
+  if ((rc = level_kparams(h, hf, &a.kh))) return rc;
+  ARG_CHECK(h, hf->d_W != nullptr && hf->N >= 1 && hf->N <= predict_small_max_n() && hf->D <= 64);
+  a.Xh = hf->d_X; a.Nh = hf->N; a.npad_h = mfgp_padded_n(hf->N); a.alpha_h = hf->d_alpha; a.Wh = hf->d_W;
+  a.noise_add = include_noise ? a.kh.noise : 0.0;
+  a.has_lf = lf != nullptr;
+  h->svc_width = hf->D;
+  if (lf) {
+    if ((rc = level_kparams(h, lf, &a.kl))) return rc;
+    ARG_CHECK(h, h_offsets && E >= 1 && E <= MFGP_MAX_E && hf->D == lf->D + E && E * lf->D <= 96 && lf->d_alpha);
+    a.Xl = lf->d_X; a.Nl = lf->N; a.alpha_l = lf->d_alpha; a.d = lf->D; a.E = E; a.tau = tau;
+    memcpy(a.offs, h_offsets, (size_t)E * lf->D * sizeof(double));
+    h->svc_width = lf->D;
+  }
+  if (!(idle_ms > 0.0)) idle_ms = 20.0;
+  a.idle_ns = (unsigned long long)(idle_ms * 1e6);
+  // the factors may still be in flight on the caller's stream
+  CUDA_TRY(h, cudaEventRecord(h->ev_la[3 * 64 + 3], h->stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->s_svc, h->ev_la[3 * 64 + 3], 0));
+  h->svc_h->stop = 0;
+  h->svc_seq = h->svc_h->ack_seq = h->svc_h->req_seq;
+  h->svc_relaunches = -1;     // the first launch is not a relaunch
+  if ((rc = point_service_relaunch(h))) return rc;
+  h->svc_relaunches = 0;
+  h->svc_active = 1;
+  return 0;
+}
+
+// One question: h_x (width doubles: plain inputs with a low-fidelity level, augmented row without) -> out[0] = mean,
+// out[1] = variance.  Spins on the mapped acknowledgement; relaunches the kernel if it left on its idle limit.
+int mfgp_point_service_eval(mfgp_handle_t h, const double* h_x, double* h_out) {
+  if (!h) return -1;
+  ARG_CHECK(h, h->svc_active && h_x && h_out);
+  PointServiceCtl* c = h->svc_h;
+  for (int i = 0; i < h->svc_width; i++) c->x[i] = h_x[i];
+  __sync_synchronize();
+  const unsigned long long seq = ++h->svc_seq;
+  c->req_seq = seq;
+  __sync_synchronize();
+  struct timespec t0;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (unsigned long long spin = 1;; spin++) {
+    if (c->ack_seq == seq) break;
+    if (!c->alive) {
+      DeviceGuard guard(h->device);
+      cudaStreamSynchronize(h->s_svc);          // the old kernel has decided to leave; let it finish
+      if (c->ack_seq == seq) break;             // it answered on its way out
+      int rc = point_service_relaunch(h);
+      if (rc) return rc;
+      h->svc_relaunches++;
+    }
+    if ((spin & 0xffff) == 0) {
+      struct timespec t1;
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) > 10.0) {
+        cudaError_t e = cudaStreamQuery(h->s_svc);
+        snprintf(h->err, sizeof(h->err), "point service: no answer within 10 s (stream state: %s)", cudaGetErrorString(e));
+        return -102;
+      }
+    }
+  }
+  __sync_synchronize();
+  h_out[0] = c->out[0];
+  h_out[1] = c->out[1];
+  return 0;
+}
+
+long long mfgp_point_service_relaunches(mfgp_handle_t h) { return h ? h->svc_relaunches : -1; }
 
 int mfgp_augment(mfgp_handle_t h, const mfgp_level_t* lf, const double* d_X, long long M,
                  const double* h_offsets, int E, double tau, double* d_Xaug, double* d_ws,

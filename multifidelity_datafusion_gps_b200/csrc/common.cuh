@@ -28,6 +28,39 @@ struct KParams {
   const double* exp_tbl;   // device, 256 doubles: 2^(j/256) (mfgp_ctx::d_exp_tbl)
 };
 
+// Point service (predict.cu: point_service_kernel).  Control block in mapped pinned host memory; every flag on its
+// own 64-byte line.
+struct PointServiceCtl {
+  volatile unsigned long long req_seq;   // host -> device: sequence number of the posted question
+  unsigned long long pad0[7];
+  volatile unsigned long long ack_seq;   // device -> host: last answered question
+  unsigned long long pad1[7];
+  volatile int stop;                     // host -> device: leave
+  int pad2[15];
+  volatile int alive;                    // 1 while a service kernel is (being) launched; the kernel clears it on exit
+  int pad3[15];
+  volatile double x[64];                 // question: query row
+  volatile double out[8];                // answer: mean, variance
+};
+struct PointServiceArgs {
+  KParams kh;
+  const double* Xh;
+  int Nh, npad_h;
+  const double* alpha_h;
+  const double* Wh;
+  int has_lf;
+  KParams kl;
+  const double* Xl;
+  int Nl;
+  const double* alpha_l;
+  int d, E;
+  double tau;
+  double offs[96];
+  double noise_add;
+  unsigned long long idle_ns;
+  unsigned long long start_seq;
+};
+
 struct mfgp_ctx {
   int device;
   cudaStream_t stream;
@@ -53,6 +86,14 @@ struct mfgp_ctx {
   cudaStream_t s_mid;                   // medium priority: the bulk updates when the caller's stream carries the
                                         // overlapped triangular inverse (potrf_trtri_padded)
   cudaEvent_t ev_la[3 * 64 + 4];
+  // point service (mfgp_point_service_*)
+  cudaStream_t s_svc;
+  PointServiceCtl* svc_h;               // mapped pinned
+  PointServiceCtl* svc_d;               // its device-side address
+  PointServiceArgs svc_args;            // kept for relaunches
+  int svc_active, svc_width;
+  unsigned long long svc_seq;
+  long long svc_relaunches;
   // optional per-kernel-class timing (mfgp_profile_enable): event pairs around launches
   int prof_on;
   cudaEvent_t* prof_ev;                 // [MFGP_PROF_CLASSES][MFGP_PROF_POOL][2]

@@ -641,19 +641,12 @@ __device__ __forceinline__ double small_kernel_value(const KParams& kp, const do
   return v;
 }
 
-// Xaug[m] = [x_m, mu_l(x_m + o_0 tau), ...]: one CTA per (row, location); fixed-order block reduction
-__global__ void __launch_bounds__(256)
-    augment_small_kernel(KParams kl, const double* __restrict__ Xl, int Nl, const double* __restrict__ alpha_l,
-                         const double* __restrict__ Xq, int d, const double* __restrict__ offs, int E,
-                         double tau, double* __restrict__ Xaug) {
-  __shared__ double stbl[256];
-  __shared__ double red[256];
-  __shared__ double loc[MFGP_MAX_D];
-  const int m = blockIdx.x / E, e = blockIdx.x - m * E, tid = threadIdx.x;
-  stbl[tid] = kl.exp_tbl[tid];
-  if (tid < d) loc[tid] = Xq[m * d + tid] + offs[e * d + tid] * tau;
-  __syncthreads();
-  const unsigned tbl = (unsigned)__cvta_generic_to_shared(stbl);
+// Block-wide pieces shared by the latency kernels and the point service (256 threads; every thread must call).
+// mu_l(loc) = sum_k K_l(loc, Xl_k) alpha_k, fixed-order block reduction; the result is returned to every thread.
+__device__ __forceinline__ double ps_lf_mean(const KParams& kl, const double* __restrict__ Xl, int Nl,
+                                             const double* __restrict__ alpha_l, const double* loc, unsigned tbl,
+                                             double* red /* [256] shared */) {
+  const int tid = threadIdx.x;
   double acc = 0.0;
   for (int k = tid; k < Nl; k += 256) acc = fma(small_kernel_value(kl, loc, Xl + (long)k * kl.D, tbl), alpha_l[k], acc);
   red[tid] = acc;
@@ -662,26 +655,18 @@ __global__ void __launch_bounds__(256)
     if (tid < o) red[tid] += red[tid + o];
     __syncthreads();
   }
-  double* row = Xaug + (long)m * (d + E);
-  if (tid == 0) row[d + e] = red[0];
-  if (e == 0 && tid < d) row[tid] = Xq[m * d + tid];
+  const double v = red[0];
+  __syncthreads();
+  return v;
 }
 
-// (mean, var) of one query row per CTA: kx in shared memory, mean by a fixed-order block reduction, then
-// tmp = W kx with one warp per row of W (coalesced), sum of squares in a fixed order
-__global__ void __launch_bounds__(256)
-    predict_small_kernel(KParams kp, const double* __restrict__ X, int N, int npad,
-                         const double* __restrict__ alpha, const double* __restrict__ W,
-                         const double* __restrict__ Xq, double noise_add, double* __restrict__ out /* (M, 2) */) {
-  __shared__ double stbl[256];
-  __shared__ double kx[PS_MAXN];
-  __shared__ double red[256];
-  __shared__ double wss[8];
+// (mean, var) of one query row q: kx in shared memory, mean by a fixed-order block reduction, then tmp = W kx with
+// one warp per row of W (coalesced), sum of squares in a fixed order.  Valid in thread 0 on return.
+__device__ __forceinline__ void ps_predict_row(const KParams& kp, const double* __restrict__ X, int N, int npad,
+                                               const double* __restrict__ alpha, const double* __restrict__ W,
+                                               const double* q, double noise_add, unsigned tbl, double* kx,
+                                               double* red, double* wss, double& mean, double& var) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double* q = Xq + (long)blockIdx.x * kp.D;
-  stbl[tid] = kp.exp_tbl[tid];
-  __syncthreads();
-  const unsigned tbl = (unsigned)__cvta_generic_to_shared(stbl);
   double acc = 0.0;
   for (int k = tid; k < N; k += 256) {
     const double v = small_kernel_value(kp, q, X + (long)k * kp.D, tbl);
@@ -705,13 +690,135 @@ __global__ void __launch_bounds__(256)
   }
   if (lane == 0) wss[warp] = ss;
   __syncthreads();
+  mean = 0.0;
+  var = 0.0;
   if (tid == 0) {
-    double s = 0.0;
-    for (int w = 0; w < 8; w++) s += wss[w];
-    double v = kp.kdiag - s;
+    double sum = 0.0;
+    for (int w = 0; w < 8; w++) sum += wss[w];
+    double v = kp.kdiag - sum;
     v = v < 1e-15 ? 1e-15 : v;   // GPy posterior.py: np.clip(var, 1e-15, inf)
-    out[2 * blockIdx.x] = red[0];
-    out[2 * blockIdx.x + 1] = v + noise_add;
+    mean = red[0];
+    var = v + noise_add;
+  }
+  __syncthreads();
+}
+
+// Xaug[m] = [x_m, mu_l(x_m + o_0 tau), ...]: one CTA per (row, location); fixed-order block reduction
+__global__ void __launch_bounds__(256)
+    augment_small_kernel(KParams kl, const double* __restrict__ Xl, int Nl, const double* __restrict__ alpha_l,
+                         const double* __restrict__ Xq, int d, const double* __restrict__ offs, int E,
+                         double tau, double* __restrict__ Xaug) {
+  __shared__ double stbl[256];
+  __shared__ double red[256];
+  __shared__ double loc[MFGP_MAX_D];
+  const int m = blockIdx.x / E, e = blockIdx.x - m * E, tid = threadIdx.x;
+  stbl[tid] = kl.exp_tbl[tid];
+  if (tid < d) loc[tid] = Xq[m * d + tid] + offs[e * d + tid] * tau;
+  __syncthreads();
+  const unsigned tbl = (unsigned)__cvta_generic_to_shared(stbl);
+  const double mu = ps_lf_mean(kl, Xl, Nl, alpha_l, loc, tbl, red);
+  double* row = Xaug + (long)m * (d + E);
+  if (tid == 0) row[d + e] = mu;
+  if (e == 0 && tid < d) row[tid] = Xq[m * d + tid];
+}
+
+// (mean, var) of one query row per CTA
+__global__ void __launch_bounds__(256)
+    predict_small_kernel(KParams kp, const double* __restrict__ X, int N, int npad,
+                         const double* __restrict__ alpha, const double* __restrict__ W,
+                         const double* __restrict__ Xq, double noise_add, double* __restrict__ out /* (M, 2) */) {
+  __shared__ double stbl[256];
+  __shared__ double kx[PS_MAXN];
+  __shared__ double red[256];
+  __shared__ double wss[8];
+  const int tid = threadIdx.x;
+  const double* q = Xq + (long)blockIdx.x * kp.D;
+  stbl[tid] = kp.exp_tbl[tid];
+  __syncthreads();
+  const unsigned tbl = (unsigned)__cvta_generic_to_shared(stbl);
+  double mean, var;
+  ps_predict_row(kp, X, N, npad, alpha, W, q, noise_add, tbl, kx, red, wss, mean, var);
+  if (tid == 0) {
+    out[2 * blockIdx.x] = mean;
+    out[2 * blockIdx.x + 1] = var;
+  }
+}
+
+// ---- point service: single-row predicts answered by a RESIDENT single-CTA kernel through mapped host memory ----
+// The reference's default acquisition (scipydirect DIRECT, src/adaptation_maximizers/scipydirect_wrapper.py:22-26)
+// asks for up to 20 000 single-point predicts ONE AFTER THE OTHER; each answer decides the next question, so they
+// cannot be batched.  Per question the launch + synchronise path costs ~30 us of driver latency for ~3 us of
+// arithmetic.  Here one CTA stays resident for the duration of a search: the host writes the query row and a
+// sequence number into mapped pinned memory, thread 0 polls that number over PCIe, the CTA evaluates the row with
+// the very device functions of the latency kernels (bit-identical results) and writes (mean, variance) and the
+// acknowledged sequence number back.  No launch, no stream synchronisation per question.  The kernel leaves on a
+// stop flag or after `idle_ns` without a question (a crashed host cannot pin the SM); the host relaunches it when
+// it finds it gone.  It occupies ONE SM and runs on its own non-blocking stream.
+__device__ __forceinline__ unsigned long long ps_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+    point_service_kernel(PointServiceArgs a, PointServiceCtl* ctl) {
+  __shared__ double stbl[256];
+  __shared__ double kx[PS_MAXN];
+  __shared__ double red[256];
+  __shared__ double wss[8];
+  __shared__ double q[MFGP_MAX_D + MFGP_MAX_E];
+  __shared__ double loc[MFGP_MAX_D];
+  __shared__ unsigned long long s_seq;
+  __shared__ int s_go;
+  const int tid = threadIdx.x;
+  stbl[tid] = a.kh.exp_tbl[tid];
+  __syncthreads();
+  const unsigned tbl = (unsigned)__cvta_generic_to_shared(stbl);
+  unsigned long long last = a.start_seq;
+  const int width = a.has_lf ? a.d : a.kh.D;
+  for (;;) {
+    if (tid == 0) {
+      const unsigned long long t0 = ps_globaltimer();
+      int go = 0;
+      unsigned long long seq = last;
+      for (unsigned spin = 0;; spin++) {
+        seq = ctl->req_seq;                     // one PCIe read per poll
+        if (seq != last) { go = 1; break; }
+        if ((spin & 15u) == 15u) {
+          if (ctl->stop) break;
+          if (ps_globaltimer() - t0 > a.idle_ns) break;
+        }
+      }
+      s_go = go;
+      s_seq = seq;
+    }
+    __syncthreads();
+    if (!s_go) break;
+    if (tid < width) q[tid] = ctl->x[tid];
+    __syncthreads();
+    if (a.has_lf) {
+      for (int e = 0; e < a.E; e++) {
+        if (tid < a.d) loc[tid] = q[tid] + a.offs[e * a.d + tid] * a.tau;
+        __syncthreads();
+        const double mu = ps_lf_mean(a.kl, a.Xl, a.Nl, a.alpha_l, loc, tbl, red);
+        if (tid == 0) q[a.d + e] = mu;
+        __syncthreads();
+      }
+    }
+    double mean, var;
+    ps_predict_row(a.kh, a.Xh, a.Nh, a.npad_h, a.alpha_h, a.Wh, q, a.noise_add, tbl, kx, red, wss, mean, var);
+    if (tid == 0) {
+      ctl->out[0] = mean;
+      ctl->out[1] = var;
+      __threadfence_system();
+      ctl->ack_seq = s_seq;
+    }
+    last = s_seq;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    __threadfence_system();
+    ctl->alive = 0;
   }
 }
 
@@ -1214,6 +1321,12 @@ int path_wsum_launch(mfgp_ctx* h, const double* mu_c, const double* w, long long
                      double* path) {
   if (npts <= 0 || S <= 0) return 0;
   path_wsum_kernel<<<S, 256, 0, h->stream>>>(mu_c, w, m_lo, npts, S, path);
+  LAUNCH_CHECK(h);
+  return 0;
+}
+
+int point_service_launch(mfgp_ctx* h, const PointServiceArgs& a, PointServiceCtl* d_ctl, cudaStream_t stream) {
+  point_service_kernel<<<1, 256, 0, stream>>>(a, d_ctl);
   LAUNCH_CHECK(h);
   return 0;
 }

@@ -857,3 +857,49 @@ def test_predict_point_latency_path_matches_predict(pkg):
             assert util.rel_err(mu_p, mu) < 1e-11 and util.rel_err(var_p, var, 1.2) < 1e-10
         mu_f, var_f = m.predict_point(rs.uniform(size=(40, 2)))               # too many rows: falls back
         assert mu_f.shape == (40, 1)
+
+
+# ---- point service: the resident single-row predictor behind the default DIRECT maximiser -----------------
+def _service_models(pkg):
+    lf_X, X_hf, _ = _data(2, n_hf=12)
+    callable_lf = pkg.GPDF(2, 0.001, 2, util.hf_2d, util.lf_2d)
+    callable_lf.fit(X_hf, theta=THETA_R)
+    data_lf = pkg.NARGP(2, util.hf_2d, None, lf_X=lf_X, lf_Y=util.lf_2d(lf_X))
+    data_lf.fit(X_hf, theta=THETA_C)
+    return callable_lf, data_lf
+
+
+def test_point_service_equals_the_latency_path_bit_for_bit(pkg):
+    import time
+    import torch
+    for m in _service_models(pkg):
+        pts = np.random.default_rng(12).uniform(size=(40, 2))
+        ref = [m.predict_point(p[None]) for p in pts]
+        assert m.point_service_start(idle_ms=2.0)
+        try:
+            got = [m.point_service_eval(p) for p in pts[:20]]
+            time.sleep(0.05)                               # the kernel leaves on its idle limit ...
+            torch.cuda.synchronize()                       # ... so a device-wide synchronisation returns
+            got += [m.point_service_eval(p) for p in pts[20:]]   # ... and the next question relaunches it
+            h = m._svc_handle
+            assert h.lib.mfgp_point_service_relaunches(h.h) >= 1
+        finally:
+            m.point_service_stop()
+        for (mu, v), (mu_r, v_r) in zip(got, ref):
+            assert mu == mu_r[0, 0] and v == v_r[0, 0]
+        mu2, v2 = m.predict(pts)                           # the ordinary path is untouched afterwards
+        assert util.rel_err(np.array([g[0] for g in got]), mu2[:, 0]) < 1e-10
+
+
+def test_direct_maximiser_through_the_service_finds_the_same_point(pkg):
+    callable_lf, _ = _service_models(pkg)
+    maxi = pkg.ScipyDirectMaximizer(maxf=600, maxT=200)
+    lo, hi = np.zeros(2), np.ones(2)
+    x_s, f_s = maxi.maximize(callable_lf.predict, lo, hi)
+    orig = callable_lf.point_service_start
+    callable_lf.point_service_start = lambda *a, **k: False     # force the latency path
+    try:
+        x_l, f_l = maxi.maximize(callable_lf.predict, lo, hi)
+    finally:
+        callable_lf.point_service_start = orig
+    assert np.array_equal(x_s, x_l) and f_s == f_l
