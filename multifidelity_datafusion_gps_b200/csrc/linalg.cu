@@ -16,6 +16,9 @@
 #ifndef MFGP_TRMM_TMA_DEFAULT
 #define MFGP_TRMM_TMA_DEFAULT 1      // measured r02: 2.42 -> 2.27 ms per 75 776 x 1024 launch, bit-identical sums
 #endif
+#ifndef MFGP_GEMM_TMA_MC_DEFAULT
+#define MFGP_GEMM_TMA_MC_DEFAULT 1
+#endif
 #ifndef MFGP_GEMM_TMA_DEFAULT
 #define MFGP_GEMM_TMA_DEFAULT 1      // measured r02 at N = 16384: potrf 53.8 -> 51.6 ms, trtri 44.7 -> 43.6, same bits
 #endif
@@ -692,6 +695,63 @@ static int try_gemm_tma(mfgp_ctx* h, const dg::GemmParams& p, int cls) {
   return 1;
 }
 
+// row-major FP64 matrix read as an m-contiguous operand X(m, k) = X[k * ld + m]: boxes of {16 m values, 32 k rows}
+static bool make_map_mc(CUtensorMap* m, const double* base, unsigned long long m_extent, unsigned long long k_rows,
+                        unsigned long long ld) {
+  EncodeTiledFn fn = encode_tiled();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {m_extent, k_rows};
+  cuuint64_t strides[1] = {ld * sizeof(double)};
+  cuuint32_t box[2] = {16, 32};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int gemm_tma_mc_enabled() {     // MFGP_GEMM_TMA_MC=0: cp.async kernels for the TN / TT / NN products
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFGP_GEMM_TMA_MC");
+    v = e ? (atoi(e) != 0) : MFGP_GEMM_TMA_MC_DEFAULT;
+  }
+  return v;
+}
+
+// Products with at least one m-contiguous operand (first product of the triangular inverse, K^-1 = W^T W,
+// the Gram / right-multiply helpers of the delayed-input MC path) through gemm_tma_mc_kernel.  Returns 1 if it
+// took the launch.
+template <bool A_KC, bool B_KC>
+static int try_gemm_tma_mc(mfgp_ctx* h, const dg::GemmParams& p, int cls) {
+  if (!gemm_tma_enabled() || !gemm_tma_mc_enabled()) return 0;
+  const int nodes = p.batch > 1 ? p.batch : 1;
+  long n_shift = 0, c_stride = 0;
+  if (nodes > 1) {
+    if (p.lda != p.ldb || p.lda != p.ldc) return 0;
+    n_shift = p.batch_stride / (p.lda + 1);
+    if (n_shift * (p.lda + 1) != p.batch_stride) return 0;
+    c_stride = p.batch_stride;
+  }
+  const unsigned long long a_m = (unsigned long long)p.M + (nodes - 1) * n_shift;
+  const unsigned long long b_n = (unsigned long long)p.N + (nodes - 1) * n_shift;
+  const unsigned long long kext = (unsigned long long)p.K + (nodes - 1) * n_shift;
+  CUtensorMap tmA, tmB;
+  const bool okA = A_KC ? make_map(&tmA, p.A, kext, a_m, p.lda) : make_map_mc(&tmA, p.A, a_m, kext, p.lda);
+  const bool okB = B_KC ? make_map(&tmB, p.B, kext, b_n, p.ldb) : make_map_mc(&tmB, p.B, b_n, kext, p.ldb);
+  if (!okA || !okB) return 0;
+  dg::GemmTmaParams q;
+  memset(&q, 0, sizeof(q));
+  q.C = p.C; q.ldc = p.ldc; q.M = p.M; q.N = p.N; q.K = p.K; q.alpha = p.alpha; q.beta = p.beta;
+  q.lower_only = p.lower_only; q.kb_row = p.kb_row; q.kb_col = p.kb_col; q.ke_row = p.ke_row;
+  q.batch = p.batch; q.c_batch_stride = c_stride;
+  q.a_batch_rows = q.a_batch_k = q.b_batch_rows = q.b_batch_k = (int)n_shift;
+  prof_begin(h, cls);
+  dg::gemm_tma_mc_kernel<dg::Big16, A_KC, B_KC>
+      <<<tile_count<dg::Big16>(p), dg::Big16::THREADS, dg::tma::SMEM_BYTES, h->stream>>>(tmA, tmB, q);
+  prof_end(h, cls);
+  return 1;
+}
+
 // Narrow GEMMs (fewer 128x128 tiles than SMs) sit on the critical path of the recursion: run them
 // with 64x64 tiles so that four times as many SMs share the work.
 template <bool A_KC, bool B_KC>
@@ -701,6 +761,12 @@ int launch_gemm(mfgp_ctx* h, const dg::GemmParams& p, int cls = PC_GEMM) {
   if (A_KC && B_KC && big_tiles >= MFGP_NUM_SMS && tile_variant() == 16 && try_gemm_tma(h, p, cls)) {
     LAUNCH_CHECK(h);
     return 0;
+  }
+  if constexpr (!(A_KC && B_KC)) {
+    if (big_tiles >= MFGP_NUM_SMS && tile_variant() == 16 && try_gemm_tma_mc<A_KC, B_KC>(h, p, cls)) {
+      LAUNCH_CHECK(h);
+      return 0;
+    }
   }
   prof_begin(h, cls);
   if (big_tiles < MFGP_NUM_SMS) {
@@ -841,6 +907,12 @@ int linalg_configure(mfgp_ctx* h) {
   CUDA_TRY(h, cudaFuncSetAttribute(dg::trmm_sumsq_tma_kernel<dg::Big16>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, dg::tma::SMEM_BYTES));
   CUDA_TRY(h, cudaFuncSetAttribute(dg::gemm_tma_kernel<dg::Big16>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::tma::SMEM_BYTES));
+  CUDA_TRY(h, cudaFuncSetAttribute(dg::gemm_tma_mc_kernel<dg::Big16, false, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::tma::SMEM_BYTES));
+  CUDA_TRY(h, cudaFuncSetAttribute(dg::gemm_tma_mc_kernel<dg::Big16, false, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, dg::tma::SMEM_BYTES));
+  CUDA_TRY(h, cudaFuncSetAttribute(dg::gemm_tma_mc_kernel<dg::Big16, true, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, dg::tma::SMEM_BYTES));
   rc |= configure_gemm<dg::Big16, true, true>(h);
   rc |= configure_gemm<dg::Big16, false, true>(h);

@@ -1,2 +1,8 @@
-timeout 300 python -m pytest tests/test_gpu_models.py -m gpu -q -x -k "point_service or direct_maximiser" > gpurun_out/r2p_pytest.log 2>&1; echo pytest rc=$?; tail -15 gpurun_out/r2p_pytest.log
-timeout 300 python tools/direct_probe.py > gpurun_out/r2p_direct.log 2>&1; echo probe rc=$?; tail -5 gpurun_out/r2p_direct.log
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x > gpurun_out/r2q_pytest.log 2>&1; echo pytest rc=$?; tail -8 gpurun_out/r2q_pytest.log
+{
+echo "== TMA_MC=1"; timeout 300 python tools/lml_probe.py 16384 3
+echo "== TMA_MC=0"; MFGP_GEMM_TMA_MC=0 timeout 300 python tools/lml_probe.py 16384 3
+echo "== TMA_MC=1 n=8192"; timeout 300 python tools/lml_probe.py 8192 2
+echo "== TMA_MC=0 n=8192"; MFGP_GEMM_TMA_MC=0 timeout 300 python tools/lml_probe.py 8192 2
+} > gpurun_out/r2q_mc.log 2>&1
+grep -v "rep 0" gpurun_out/r2q_mc.log
