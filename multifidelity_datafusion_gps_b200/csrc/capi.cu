@@ -6,7 +6,7 @@
 
 // launchers defined in predict.cu
 int solve_alpha_launch(mfgp_ctx* h, const double* L, const double* W, int npad, int N,
-                       const double* y, double* v_tmp, double* alpha, double* d_out3);
+                       const double* y, double* v_tmp, double* alpha, double* d_out3, int ldl);
 int cross_gen_launch(mfgp_ctx* h, const KParams& kp, const double* X, int N, int npad,
                      const double* alpha, const double* Xq, long long ncols, long long cols_pad,
                      double* Ks, double* mean);
@@ -324,7 +324,7 @@ int mfgp_assemble(mfgp_handle_t h, int kind, const double* d_X, int N, int D, in
 // shared by factorize / lml_grad: returns after enqueueing; scalars at d_scalars[0..2]
 static int factor_enqueue(mfgp_ctx* h, const KParams& kp, const double* d_X, const double* d_y, int N,
                           double jitter, double* d_A, double* d_W, double* d_alpha,
-                          cudaEvent_t* ev /* optional, 5 events */) {
+                          cudaEvent_t* ev /* optional, 5 events */, bool defer_solve = false) {
   const int npad = mfgp_padded_n(N);
   ARG_CHECK(h, npad <= MFGP_PARTIALS);
   int rc;
@@ -336,7 +336,8 @@ static int factor_enqueue(mfgp_ctx* h, const KParams& kp, const double* d_X, con
   // (ev[2] sits where the factorisation is complete; part of the inverse may already have run by then)
   if ((rc = potrf_trtri_padded(h, d_A, d_W, npad, N, ev ? ev[2] : nullptr))) return rc;
   if (ev) CUDA_TRY(h, cudaEventRecord(ev[3], h->stream));
-  if ((rc = solve_alpha_launch(h, d_A, d_W, npad, N, d_y, h->d_partials, d_alpha, h->d_scalars)))
+  if (defer_solve) return 0;
+  if ((rc = solve_alpha_launch(h, d_A, d_W, npad, N, d_y, h->d_partials, d_alpha, h->d_scalars, npad)))
     return rc;
   if (ev) CUDA_TRY(h, cudaEventRecord(ev[4], h->stream));
   return 0;
@@ -404,8 +405,31 @@ int mfgp_lml_grad_timed(mfgp_handle_t h, int kind, const double* d_X, const doub
     return h->h_info[0];
   }
   cudaEvent_t* ev = h_ms ? h->ev : nullptr;
-  if ((rc = factor_enqueue(h, kp, d_X, d_y, N, jitter, d_A, d_W, d_alpha, ev))) return rc;
-  if ((rc = lauum_padded(h, d_W, d_A, npad))) return rc;
+  // Untimed (production) schedule: the O(N^2), HBM-bound solves (v = W y, alpha = W^T v, LML) run on the side stream
+  // UNDER the tensor-bound K^-1 = W^T W -- both only read W.  With stage timing the schedule stays sequential so
+  // that the six stage times add up.
+  static const bool overlap_solve = !(getenv("MFGP_OVERLAP_SOLVE") && atoi(getenv("MFGP_OVERLAP_SOLVE")) == 0);
+  if (!ev && overlap_solve && h->s_hi && npad >= 2048 && 2LL * npad <= MFGP_PARTIALS) {
+    if ((rc = factor_enqueue(h, kp, d_X, d_y, N, jitter, d_A, d_W, d_alpha, nullptr, true))) return rc;
+    cudaStream_t caller = h->stream;
+    cudaEvent_t ev_fork = h->ev_la[3 * 64], ev_join = h->ev_la[3 * 64 + 1];
+    // the log-determinant needs the diagonal of L, which K^-1 is about to overwrite: packed copy first
+    double* diag = h->d_partials + npad;
+    CUDA_TRY(h, cudaMemcpy2DAsync(diag, sizeof(double), d_A, (size_t)(npad + 1) * sizeof(double), sizeof(double),
+                                  (size_t)N, cudaMemcpyDeviceToDevice, caller));
+    CUDA_TRY(h, cudaEventRecord(ev_fork, caller));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->s_hi, ev_fork, 0));
+    h->stream = h->s_hi;
+    rc = solve_alpha_launch(h, diag, d_W, npad, N, d_y, h->d_partials, d_alpha, h->d_scalars, 0);
+    h->stream = caller;
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(ev_join, h->s_hi));
+    if ((rc = lauum_padded(h, d_W, d_A, npad))) return rc;
+    CUDA_TRY(h, cudaStreamWaitEvent(caller, ev_join, 0));
+  } else {
+    if ((rc = factor_enqueue(h, kp, d_X, d_y, N, jitter, d_A, d_W, d_alpha, ev))) return rc;
+    if ((rc = lauum_padded(h, d_W, d_A, npad))) return rc;
+  }
   if (ev) CUDA_TRY(h, cudaEventRecord(ev[5], h->stream));
   if ((rc = grad_reduce_launch(h, kp, d_X, N, d_A, npad, d_alpha, h->d_scalars + 8))) return rc;
   if (ev) CUDA_TRY(h, cudaEventRecord(ev[6], h->stream));
@@ -479,7 +503,7 @@ int mfgp_append_point(mfgp_handle_t h, int kind, const double* d_X, const double
   if ((rc = append_point_launch(h, krow, N, npad, kp.kdiag + kp.noise + JITTER_CONST + jitter, d_A, d_W,
                                 a_holds_L, l_tmp, t_tmp, h->d_scalars + 32)))
     return rc;
-  if ((rc = solve_alpha_launch(h, d_A, d_W, npad, N + 1, d_y, h->d_partials, d_alpha, h->d_scalars))) return rc;
+  if ((rc = solve_alpha_launch(h, d_A, d_W, npad, N + 1, d_y, h->d_partials, d_alpha, h->d_scalars, npad))) return rc;
   if ((rc = fetch_scalars(h, 40))) return rc;
   if (h_out) {
     h_out[0] = a_holds_L ? h->h_pinned[0] : NAN;   // LML of the N+1 points

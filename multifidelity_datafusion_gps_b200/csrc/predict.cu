@@ -1046,13 +1046,15 @@ inline unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 }  // namespace
 
 // ---- host launchers ----------------------------------------------------------------------------
+// ldl: row stride of L for the diagonal L[i * ldl + i] of the log-determinant (npad for the factor itself; 0 when
+// L points at a packed copy of the diagonal)
 int solve_alpha_launch(mfgp_ctx* h, const double* L, const double* W, int npad, int N,
-                       const double* y, double* v_tmp, double* alpha, double* d_out3) {
+                       const double* y, double* v_tmp, double* alpha, double* d_out3, int ldl) {
   trmv_lower_kernel<<<nblk(npad, 8), 256, 0, h->stream>>>(W, npad, y, N, v_tmp);
   LAUNCH_CHECK(h);
   trmv_lower_t_kernel<<<npad / 32, 256, 0, h->stream>>>(W, npad, v_tmp, alpha);
   LAUNCH_CHECK(h);
-  lml_kernel<<<1, 256, 0, h->stream>>>(L, npad, N, y, alpha, d_out3);
+  lml_kernel<<<1, 256, 0, h->stream>>>(L, ldl, N, y, alpha, d_out3);
   LAUNCH_CHECK(h);
   return 0;
 }
