@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x > gpurun_out/r2r_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/r2r_pytest.log
-timeout 300 python tools/lml_total_probe.py 16384 2>&1 | tail -6
-timeout 300 python tools/lml_total_probe.py 8192 2>&1 | tail -6
-timeout 300 python tools/lml_total_probe.py 2500 2>&1 | tail -6
+python -m pytest tests -m gpu -q -x > gpurun_out/r2s_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/r2s_pytest.log
+python bench.py > gpurun_out/r2s_bench.json 2> gpurun_out/r2s_bench.err; echo bench rc=$?
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2s_bench_reference.json 2> gpurun_out/r2s_bench_reference.err; echo ref rc=$?
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2s_smoke.log 2>&1; echo smoke rc=$?; tail -1 gpurun_out/r2s_smoke.log
