@@ -200,6 +200,10 @@ __global__ void build_mc_rows_kernel(const double* __restrict__ Xtest, const dou
 // sized by S leave room for four CTAs per SM at S = 100 (50 KB each) instead of two (80 KB).
 constexpr int MC_KCHUNK = 512;    // k values staged per pass (static smem)
 constexpr int MC_MAXS = 1024;
+#ifndef MFGP_MC_SB
+#define MFGP_MC_SB 2
+#endif
+constexpr int MC_SB = MFGP_MC_SB;  // samples sharing one pass over the staged chunk
 
 __global__ void __launch_bounds__(256)
     cross_gen_mc_kernel(KParams kp, const double* __restrict__ X, int N, int npad,
@@ -258,10 +262,20 @@ __global__ void __launch_bounds__(256)
       }
     }
     __syncthreads();
-    for (int s = warp; s < S; s += 8) {
-      const double z = zs[s];
-      double* row = Ks + ((long long)blockIdx.x * S + s) * npad + k0;
-      double acc = 0.0;
+    // MC_SB samples per pass over the staged chunk: the four shared-memory operands of an element pair are loaded
+    // once for all of them (ncu r02: the kernel was bound by shared-memory wavefronts -- short-scoreboard stalls,
+    // LSU 58 % busy -- not by the FP64 pipe or HBM); per sample the arithmetic and its order are unchanged
+    for (int s0 = warp * MC_SB; s0 < S; s0 += 8 * MC_SB) {
+      double z[MC_SB], acc[MC_SB];
+      double* row[MC_SB];
+      bool live[MC_SB];
+#pragma unroll
+      for (int q = 0; q < MC_SB; q++) {
+        live[q] = s0 + q < S;
+        z[q] = live[q] ? zs[s0 + q] : 0.0;
+        acc[q] = 0.0;
+        row[q] = Ks + ((long long)blockIdx.x * S + (live[q] ? s0 + q : s0)) * npad + k0;
+      }
       const int kval = min(klen, N - k0);        // training points in this chunk (the rest is pad)
       const int kfull = kval & ~1;
       for (int kk = 2 * lane; kk < kfull; kk += 64) {
@@ -269,27 +283,39 @@ __global__ void __launch_bounds__(256)
         const double2 v = *reinterpret_cast<const double2*>(sv + kk);
         const double2 zz = *reinterpret_cast<const double2*>(sz + kk);
         const double2 a = *reinterpret_cast<const double2*>(sa + kk);
-        const double t0 = z - zz.x, t1 = z - zz.y;
-        double2 o;
-        o.x = fm::exp2s(fma(uz * t0, t0, u.x), tbl) + v.x;
-        o.y = fm::exp2s(fma(uz * t1, t1, u.y), tbl) + v.y;
-        *reinterpret_cast<double2*>(row + kk) = o;
-        acc = fma(o.x, a.x, acc);
-        acc = fma(o.y, a.y, acc);
+#pragma unroll
+        for (int q = 0; q < MC_SB; q++) {
+          if (!live[q]) continue;
+          const double t0 = z[q] - zz.x, t1 = z[q] - zz.y;
+          double2 o;
+          o.x = fm::exp2s(fma(uz * t0, t0, u.x), tbl) + v.x;
+          o.y = fm::exp2s(fma(uz * t1, t1, u.y), tbl) + v.y;
+          *reinterpret_cast<double2*>(row[q] + kk) = o;
+          acc[q] = fma(o.x, a.x, acc[q]);
+          acc[q] = fma(o.y, a.y, acc[q]);
+        }
       }
       // ragged end: at most one training point, then the zero pad up to the 128-multiple
       for (int kk = kfull + 2 * lane; kk < klen; kk += 64) {
-        double2 o = make_double2(0.0, 0.0);
-        if (kk < kval) {
-          const double t0 = z - sz[kk];
-          o.x = fm::exp2s(fma(uz * t0, t0, su[kk]), tbl) + sv[kk];
-          acc = fma(o.x, sa[kk], acc);
+#pragma unroll
+        for (int q = 0; q < MC_SB; q++) {
+          if (!live[q]) continue;
+          double2 o = make_double2(0.0, 0.0);
+          if (kk < kval) {
+            const double t0 = z[q] - sz[kk];
+            o.x = fm::exp2s(fma(uz * t0, t0, su[kk]), tbl) + sv[kk];
+            acc[q] = fma(o.x, sa[kk], acc[q]);
+          }
+          *reinterpret_cast<double2*>(row[q] + kk) = o;
         }
-        *reinterpret_cast<double2*>(row + kk) = o;
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) macc[s] += acc;   // warp `s % 8` is the only writer of macc[s]
+      for (int q = 0; q < MC_SB; q++) {
+        double r = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        if (lane == 0 && live[q]) macc[s0 + q] += r;   // one warp is the only writer of macc[s]
+      }
     }
   }
   __syncthreads();

@@ -1,4 +1,8 @@
-python -m pytest tests -m gpu -q -x > gpurun_out/r2s_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/r2s_pytest.log
-python bench.py > gpurun_out/r2s_bench.json 2> gpurun_out/r2s_bench.err; echo bench rc=$?
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2s_bench_reference.json 2> gpurun_out/r2s_bench_reference.err; echo ref rc=$?
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2s_smoke.log 2>&1; echo smoke rc=$?; tail -1 gpurun_out/r2s_smoke.log
+timeout 600 python -m pytest tests/test_gpu_models.py -m gpu -q -x -k "mc" > gpurun_out/r2t_pytest.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/r2t_pytest.log
+for v in default sb1 sb4; do
+  if [ $v = default ]; then unset MFGP_LIB; else export MFGP_LIB=tools/variants/libmfgp_$v.so; fi
+  python bench.py --steps 2 --warmup 1 --no-extras --no-lml --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$v', 'value %.4e'%d['value'], 'ms %.1f'%d['ms_per_step'], d['roofline']['other_kernels_ms_per_launch'], 'pce %.15g'%d['pce_mean'])"
+done
