@@ -26,6 +26,21 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.mfgp_version() == 100
 
 
+def test_mc_scratch_size_helper_is_pure_host_logic():
+    """mfgp_predict_mc_ws_bytes: three doubles per (point, sample) column when every upper level is small enough for
+    the fused kernel, four 128-column tiles per SM of padded rows otherwise; never less than one point's samples."""
+    from multifidelity_datafusion_gps_b200 import _ffi
+    lib = _ffi.load_library()
+    f = lib.mfgp_predict_mc_ws_bytes
+    M, S, d = 1 << 20, 100, 4
+    small, general = f(100, 30, d, M, S), f(100, 1024, d, M, S)
+    assert small >= 16 * M + 24 * M * S                                  # whole batch in one launch
+    assert general >= 16 * M + 148 * 128 * 4 * (1024 + d + 4) * 8        # four tiles per SM
+    assert f(4096, 1024, d, M, S) >= 16 * M + (4096 + 1) * 148 * 128 * 4 * 8   # the LF stage gets the same
+    assert f(100, 30, d, 1 << 26, 1000) <= (12 << 30)                    # capped; the call then walks in chunks
+    assert f(100, 65, d, 10, 7) >= (7 + 256) * (128 + d + 4) * 8         # minimum: one point's samples
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
