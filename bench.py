@@ -354,6 +354,36 @@ def lml_grad_section(torch, pkg_ops, peaks, fp64_peak, n=16384, cpu=True):
             del ref
         except Exception as exc:      # the baseline is a report, not a dependency of the metric
             out["cpu_baseline"] = {"error": repr(exc)}
+    if cpu:
+        # the same comparison at N = 1024 and 4096 (the chain-bound sizes)
+        out["other_sizes"] = []
+        for n2 in (1024, 4096):
+            try:
+                from oracle import gpy_oracle as go
+                X2 = rng.uniform(size=(n2, 4))
+                Xa2 = np.concatenate([X2, lf_4d(X2)], axis=1)
+                y2 = hf_4d(X2)
+                th2 = np.array([1.0, 0.3, 1.0, 0.3, 0.1, 0.3, 0.01 * y2.var()])
+                dX2, dy2 = torch.from_numpy(Xa2).cuda(), torch.from_numpy(y2.ravel().copy()).cuda()
+                buf2 = pkg_ops.FactorBuffers(n2, "cuda")
+                pkg_ops.lml_grad(dX2, dy2, _ffi.KIND_COMPOSITE, 4, th2, buf2)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    l2, g2, i2 = pkg_ops.lml_grad(dX2, dy2, _ffi.KIND_COMPOSITE, 4, th2, buf2)[:3]
+                gpu_ms = 1e2 * (time.perf_counter() - t0)
+                t0 = time.perf_counter()
+                ref2 = go.inference(go.KIND_COMPOSITE, Xa2, y2, 4, th2)
+                cpu_ms = 1e3 * (time.perf_counter() - t0)
+                out["other_sizes"].append({
+                    "n": n2, "gpu_ms_per_eval": gpu_ms, "cpu_ms_per_eval": cpu_ms, "speedup": cpu_ms / gpu_ms,
+                    "cores": blas_threads(), "kind": "port",
+                    "lml_rel_diff": abs(l2 - ref2["lml"]) / abs(ref2["lml"]),
+                    "grad_rel_diff": float(np.max(np.abs(g2 - ref2["grad"])) / np.max(np.abs(ref2["grad"])))})
+                del buf2, dX2, dy2, ref2
+            except Exception as exc:
+                out["other_sizes"].append({"n": n2, "error": repr(exc)})
+        torch.cuda.empty_cache()
     return out
 
 
