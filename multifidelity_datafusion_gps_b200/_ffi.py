@@ -138,6 +138,7 @@ class Handle:
                             (rc, self.lib.mfgp_last_error(None).decode()))
         self.h = h
         self.device = int(device)
+        self._stream_ptr = None                 # stream the C side is bound to (get_handle keeps it current)
 
     def close(self):
         if getattr(self, "h", None):
@@ -196,7 +197,10 @@ def get_handle(device=0):
     if h is None:
         with _handles_lock:
             h = _handles[key] = Handle(int(device))
-    h.set_stream(torch.cuda.current_stream(int(device)).cuda_stream)
+    sp = torch.cuda.current_stream(int(device)).cuda_stream
+    if sp != h._stream_ptr:                     # (re)bind only when torch's current stream changed
+        h.set_stream(sp)
+        h._stream_ptr = sp
     return h
 
 

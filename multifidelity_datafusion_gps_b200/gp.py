@@ -171,6 +171,8 @@ def _lockstep_enabled():
 class GPRegression:
     """GPy.models.GPRegression look-alike running on one B200."""
 
+    _opt_handle = None          # the calling thread's handle while optimize() runs (saves a look-up per evaluation)
+
     def __init__(self, X, Y, kernel=None, initialize=True, device=None):
         X = np.ascontiguousarray(X, dtype=np.float64)
         Y = np.ascontiguousarray(Y, dtype=np.float64)
@@ -397,7 +399,7 @@ class GPRegression:
             if getattr(self, "N", SMALL_BATCH_N + 1) <= SMALL_BATCH_N and _small_batch_enabled():
                 # the reference's own sizes: scalars-only kernel (no factors written; the posterior is
                 # rebuilt once, after the optimiser has finished)
-                lml_b, g_b, info = self.lml_and_grad_batch(theta[None, :])
+                lml_b, g_b, info = self.lml_and_grad_batch(theta[None, :], handle=self._opt_handle)
                 lml, g = (float(lml_b[0]), g_b[0]) if info[0] == 0 else self.lml_and_grad(theta)
             else:
                 lml, g = self.lml_and_grad(theta)
@@ -422,11 +424,16 @@ class GPRegression:
     def optimize(self, optimizer=None, max_iters=1000, messages=False, **kw):
         free = ~self._fixed
         x0 = logexp_finv(self.param_array[free])
-        x_opt, _, _ = self._minimise(self._objective_grads, x0, max_iters)
-        # paramz opt_lbfgsb.opt: self.f_opt = f_fp(self.x_opt)[0] -- the objective is evaluated once more at the
-        # returned point (after an abnormal line-search exit SciPy's own f is the last TRIAL point's), and
-        # that value is what optimize_restarts compares  [paramz-recall]
-        f_opt = self._objective_grads(np.array(x_opt, dtype=np.float64))[0]
+        # one handle look-up (and stream binding) per optimisation instead of one per evaluation
+        self._opt_handle = _ffi.get_handle(self.device)
+        try:
+            x_opt, _, _ = self._minimise(self._objective_grads, x0, max_iters)
+            # paramz opt_lbfgsb.opt: self.f_opt = f_fp(self.x_opt)[0] -- the objective is evaluated once more at
+            # the returned point (after an abnormal line-search exit SciPy's own f is the last TRIAL point's),
+            # and that value is what optimize_restarts compares  [paramz-recall]
+            f_opt = self._objective_grads(np.array(x_opt, dtype=np.float64))[0]
+        finally:
+            self._opt_handle = None
         theta = self.param_array
         theta[free] = logexp_f(x_opt)
         self._set_params(theta)
@@ -571,11 +578,12 @@ class GPRegression:
                                      else logexp_finv(logexp_f(starts[i])), max_iters, max_iters) for i in indices}
         fails = {i: 0 for i in indices}
         errors = {}
+        handle = _ffi.get_handle(self.device)      # one look-up (and stream binding) for the whole optimisation
         while True:
             want = [i for i in indices if i not in errors and runs[i].advance()]
             if not want:
                 break
-            vals = self._objective_batch(thetas_of([runs[i].x for i in want]), free)
+            vals = self._objective_batch(thetas_of([runs[i].x for i in want]), free, handle=handle)
             for i, v in zip(want, vals):
                 if v is None:
                     if fails[i] >= 10:                     # paramz: more than ten failures in a row re-raise
@@ -591,7 +599,7 @@ class GPRegression:
             raise errors[min(errors)]
         done = [i for i in indices if i not in errors]
         # paramz opt_lbfgsb.opt: f_opt = f_fp(x_opt)[0], for all runs in one more batched launch
-        final = self._objective_batch(thetas_of([runs[i].x for i in done]), free) if done else []
+        final = self._objective_batch(thetas_of([runs[i].x for i in done]), free, handle=handle) if done else []
         return [(i, (v[0] if v is not None else np.inf), np.array(runs[i].x, dtype=np.float64))
                 for i, v in zip(done, final)]
 
