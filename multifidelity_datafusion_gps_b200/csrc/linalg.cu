@@ -16,6 +16,9 @@
 #ifndef MFGP_TRMM_TMA_DEFAULT
 #define MFGP_TRMM_TMA_DEFAULT 1      // measured r02: 2.42 -> 2.27 ms per 75 776 x 1024 launch, bit-identical sums
 #endif
+#ifndef MFGP_NARROW_BIG_M_DEFAULT
+#define MFGP_NARROW_BIG_M_DEFAULT 6144      // measured r02 at N = 16384: potrf 50.3 -> 48.7 ms (8192: 49.0, 4096: 48.9, 2048: 49.5, 0: 50.0)
+#endif
 #ifndef MFGP_GEMM_TMA_MC_DEFAULT
 #define MFGP_GEMM_TMA_MC_DEFAULT 1
 #endif
@@ -754,11 +757,26 @@ static int try_gemm_tma_mc(mfgp_ctx* h, const dg::GemmParams& p, int cls) {
 
 // Narrow GEMMs (fewer 128x128 tiles than SMs) sit on the critical path of the recursion: run them
 // with 64x64 tiles so that four times as many SMs share the work.
+// Narrow products of the Cholesky panel (row solves, in-panel updates: fewer 128 x 128 tiles than SMs).  With many
+// rows below the panel the bulk update hides the panel, and what these products cost is MACHINE time: full 128 x 128
+// TMA tiles (one CTA per 128 rows) do the same flops on a quarter of the SM time of the 64 x 64 / 32 x 128 latency
+// tiles, which are kept for the chain-bound tail.  MFGP_NARROW_BIG_M = rows from which the big tiles are used.
+static int narrow_big_rows() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MFGP_NARROW_BIG_M");
+    v = e ? atoi(e) : MFGP_NARROW_BIG_M_DEFAULT;
+    if (v < 0) v = 1 << 30;
+  }
+  return v;
+}
+
 template <bool A_KC, bool B_KC>
 int launch_gemm(mfgp_ctx* h, const dg::GemmParams& p, int cls = PC_GEMM) {
   const int big_tiles = tile_count<dg::Big>(p);
   if (big_tiles <= 0) return 0;
-  if (A_KC && B_KC && big_tiles >= MFGP_NUM_SMS && tile_variant() == 16 && try_gemm_tma(h, p, cls)) {
+  if (A_KC && B_KC && tile_variant() == 16 &&
+      (big_tiles >= MFGP_NUM_SMS || (p.batch <= 1 && p.M >= narrow_big_rows())) && try_gemm_tma(h, p, cls)) {
     LAUNCH_CHECK(h);
     return 0;
   }
@@ -786,6 +804,11 @@ int launch_gemm(mfgp_ctx* h, const dg::GemmParams& p, int cls = PC_GEMM) {
 
 // X <- X * Wl^T in place (X: m x 128, Wl: 128 x 128): every CTA must own all 128 columns of its rows
 int launch_trsm_leaf(mfgp_ctx* h, const dg::GemmParams& p) {
+  // (in place is safe with the TMA kernel too: a CTA owns all 128 columns of its rows and stores after its last slab)
+  if (tile_variant() == 16 && p.M >= narrow_big_rows() && try_gemm_tma(h, p, PC_GEMM)) {
+    LAUNCH_CHECK(h);
+    return 0;
+  }
   prof_begin(h, PC_GEMM);
   if (p.M / 128 < MFGP_NUM_SMS) {
     dg::gemm_kernel<dg::Row32, true, true>
