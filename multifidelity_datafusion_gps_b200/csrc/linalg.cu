@@ -961,7 +961,9 @@ constexpr int LA_MAXP = 64;
 // the recursion loses at every size (its half-size TRSM / SYRK expose MORE serial leaf chain, not less), so the
 // switch stays off; kept for the record and for other shapes.
 static int LA_TAIL = 0;
-static int la_nb(int npad) { return LA_NB_ENV ? LA_NB_ENV : (npad <= 512 * LA_MAXP ? 512 : 1024); }
+// (r02, with the big-tile policy for hidden panels: N = 16384: 512 -> 49.0 ms, 640 -> 49.0, 768 -> 49.4, 1024 -> 50.0;
+//  N = 32768: 512 -> 353.6 ms, 1024 -> 344.8)
+static int la_nb(int npad) { return LA_NB_ENV ? LA_NB_ENV : (npad < 24576 ? 512 : 1024); }
 
 // The panel's critical path, 128 columns at a time (left-looking inside the panel): leaf -> ONE in-place
 // multiply of ALL rows below by the leaf inverse -> ONE update of the next 128-column block by the panel
