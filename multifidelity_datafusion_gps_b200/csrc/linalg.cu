@@ -1143,8 +1143,10 @@ int trtri_padded(mfgp_ctx* h, const double* L, double* W, int npad) {
 // the trailing updates no longer fill the machine.  The triangular inverse of the LEADING half only needs
 // L[0:n/2, 0:n/2], final once the panel ending at n/2 has been solved, so its GEMMs (1/8 of the inverse's flops
 // at n = 16384) go to the caller's stream -- lowest priority -- right behind that panel's event, while the bulk
-// updates move to a medium-priority stream and the chain keeps the high-priority one.  Results are bit-identical
-// to potrf_padded + trtri_padded (same kernels on the same data; only the schedule differs).
+// updates move to a medium-priority stream and the chain keeps the high-priority one.  Same products on the same
+// data as potrf_padded + trtri_padded; a level batched over half of the matrix may fall below one wave of tiles
+// and then takes another GEMM kernel than the level batched over the whole matrix, so the two schedules agree to
+// round-off (bit for bit with MFGP_GEMM_TMA_MC=0, where every kernel sums k in the same order).
 // MFGP_OVERLAP_TRTRI=0 switches the overlap off.
 int potrf_trtri_padded(mfgp_ctx* h, double* A, double* W, int npad, int nreal, cudaEvent_t ev_mid) {
   static int overlap = -1;
