@@ -13,8 +13,11 @@ in this image and not installable (no network), and the reference's tests hold n
 golden vectors for this boundary.  This file therefore restates
 GPy's *published algorithm* from memory of the upstream sources named below; it is
 validated by finite differences, closed-form 1-/2-point GP cases and a second,
-independently written direct-solve formulation (``tests/test_oracle.py``), not by the
-reference's own outputs.  (What the reference itself owns -- the orchestration around this
+independently written direct-solve formulation and -- since round 2 -- scikit-learn's exact
+GP as a third-party implementation of the same mathematics (LML, every hyper-parameter gradient,
+predictive mean and variance, RBF and composite kernel; ``tests/test_oracle.py``), not by the
+reference's own outputs: GPy's constants (the 1e-8 added to the diagonal, the jitchol schedule,
+the 1e-15 variance clip) remain recalled.  (What the reference itself owns -- the orchestration around this
 engine -- IS pinned by executing its code over this module: see ``oracle/mfgp_oracle.py``.)
 
 Upstream files followed, by name (GPy 1.9.9):
